@@ -1,0 +1,175 @@
+"""CPU oracles -- TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this
+package.  The product path (deepi2p_b200/) never does; it fails loudly when its CUDA
+library is missing instead of falling back to anything here.
+
+PARITY UNPINNED for the solver: the reference's solvePGivenK delegates to Ceres, which is
+not available offline, and the reference has no golden vectors.  See the
+header of frustum_oracle.cpp for what is restated and from where.
+"""
+import ctypes
+import math
+import os
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_libs = {}
+
+STAT_FIELDS = ("iterations", "successful_steps", "unique_evals", "cost_evals", "jac_evals",
+               "line_search_steps", "termination", "reserved")
+
+
+def _lib(name):
+    if name not in _libs:
+        out = _build.build()
+        _libs[name] = ctypes.CDLL(os.path.join(out, name))
+    return _libs[name]
+
+
+def _p(a, t):
+    return a.ctypes.data_as(ctypes.POINTER(t))
+
+
+def _prep_points(points):
+    pts = np.ascontiguousarray(np.asarray(points, dtype=np.float64))
+    if pts.ndim != 2 or pts.shape[0] != 3:
+        raise ValueError("points must be 3xN")
+    return pts
+
+
+def solve(points, labels, K, init_y_angle, init_T, H, W, t_lb, t_ub, max_iter=500, is_2d=True,
+          want_residuals=True):
+    """Oracle for FrustumRegistration.solvePGivenK (registration.cpp:9-186).
+
+    Returns (P 4x4, final_cost, residuals, stats dict, params[6]).
+    """
+    lib = _lib("libfrustum_oracle.so")
+    pts = _prep_points(points)
+    n = pts.shape[1]
+    lab = np.ascontiguousarray(np.asarray(labels).astype(np.int32))
+    K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    T = np.ascontiguousarray(np.asarray(init_T, dtype=np.float64).reshape(3))
+    lb = np.ascontiguousarray(np.asarray(t_lb, dtype=np.float64).reshape(3))
+    ub = np.ascontiguousarray(np.asarray(t_ub, dtype=np.float64).reshape(3))
+    P16 = np.zeros(16)
+    cost = ctypes.c_double(0.0)
+    lib.frustum_oracle_num_residuals.restype = ctypes.c_int64
+    rows = lib.frustum_oracle_num_residuals(_p(lab, ctypes.c_int32), ctypes.c_int64(n))
+    res = np.zeros(rows) if want_residuals else None
+    stats = np.zeros(8, dtype=np.int32)
+    params = np.zeros(6)
+    lib.frustum_oracle_solve(
+        _p(pts, ctypes.c_double), _p(lab, ctypes.c_int32), ctypes.c_int64(n), _p(K9, ctypes.c_double),
+        ctypes.c_double(float(init_y_angle)), _p(T, ctypes.c_double), ctypes.c_double(float(H)),
+        ctypes.c_double(float(W)), _p(lb, ctypes.c_double), _p(ub, ctypes.c_double),
+        ctypes.c_int(int(max_iter)), ctypes.c_int(1 if is_2d else 0), _p(P16, ctypes.c_double),
+        ctypes.byref(cost), _p(res, ctypes.c_double) if want_residuals else None,
+        _p(stats, ctypes.c_int32), _p(params, ctypes.c_double))
+    return P16.reshape(4, 4), cost.value, res, dict(zip(STAT_FIELDS, stats.tolist())), params
+
+
+def evaluate(points, labels, K, x, H, W, is_2d=True):
+    """cost, g = J^T r, JtJ at parameter vector x (dual-number evaluation)."""
+    lib = _lib("libfrustum_oracle.so")
+    pts = _prep_points(points)
+    n = pts.shape[1]
+    lab = np.ascontiguousarray(np.asarray(labels).astype(np.int32))
+    K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    P = 4 if is_2d else 6
+    xx = np.zeros(6)
+    xx[:P] = np.asarray(x, dtype=np.float64)[:P]
+    cost = ctypes.c_double(0.0)
+    g = np.zeros(P)
+    JtJ = np.zeros((P, P))
+    lib.frustum_oracle_evaluate(
+        _p(pts, ctypes.c_double), _p(lab, ctypes.c_int32), ctypes.c_int64(n), _p(K9, ctypes.c_double),
+        _p(xx, ctypes.c_double), ctypes.c_double(float(H)), ctypes.c_double(float(W)),
+        ctypes.c_int(1 if is_2d else 0), ctypes.byref(cost), _p(g, ctypes.c_double),
+        _p(JtJ, ctypes.c_double), None)
+    return cost.value, g, JtJ
+
+
+def wrap_in_pi(x):
+    """registration_lsq.py:189-193."""
+    x = math.fmod(x + math.pi, math.pi * 2)
+    if x < 0:
+        x += math.pi * 2
+    return x - math.pi
+
+
+def ry_matrix(a):
+    """Rotation about +y (data/augmentation.py:18-20 convention)."""
+    c, s = math.cos(a), math.sin(a)
+    return np.array([[c, 0.0, s], [0.0, 1.0, 0.0], [-s, 0.0, c]])
+
+
+def initial_guess(points, pred):
+    """get_initial_guess (registration_lsq.py:196-220): heading of the mean predicted-inside
+    point, and the 'front' filter.  Returns (init_y_angle, points_front, pred_front, mask)."""
+    pts = np.asarray(points, dtype=np.float64)
+    pred = np.asarray(pred)
+    inside = pred == 1
+    mean = pts[:, inside].mean(axis=1)
+    init_y = wrap_in_pi(math.atan2(mean[2], mean[0]) - math.pi / 2)
+    R1 = ry_matrix(init_y)
+    rp = R1 @ pts
+    zmin = rp[2, inside].min()
+    mask = rp[2, :] > zmin - 10
+    return init_y, pts[:, mask], pred[mask], mask
+
+
+def solve_multistart(points, labels, K, init_ry, init_t, H, W, t_lb, t_ub, max_iter=500, is_2d=True,
+                     threads=1):
+    """Multi-start driver (registration_lsq.py:142-186) over MATERIALISED inits
+    init_ry [I], init_t [I,3].  Deterministic arg-min (lowest index wins ties; the reference's
+    winner is racy).  Returns dict(P, cost, best, costs[I], params[I,6], stats[list])."""
+    init_ry = np.asarray(init_ry, dtype=np.float64)
+    init_t = np.asarray(init_t, dtype=np.float64)
+    I = init_ry.shape[0]
+
+    def one(i):
+        return solve(points, labels, K, init_ry[i], init_t[i], H, W, t_lb, t_ub, max_iter, is_2d,
+                     want_residuals=False)
+
+    if threads > 1:
+        with ThreadPoolExecutor(threads) as ex:
+            outs = list(ex.map(one, range(I)))
+    else:
+        outs = [one(i) for i in range(I)]
+    costs = np.array([o[1] for o in outs])
+    best = int(np.argmin(costs))       # first minimum
+    return dict(P=outs[best][0], cost=float(costs[best]), best=best, costs=costs,
+                params=np.stack([o[4] for o in outs]), stats=[o[3] for o in outs],
+                poses=np.stack([o[0] for o in outs]))
+
+
+def index_max(data, index, K):
+    """Oracle for index_max.forward_* (index_max.cpp:73-112)."""
+    lib = _lib("libops_oracle.so")
+    data = np.ascontiguousarray(np.asarray(data, dtype=np.float32))
+    index = np.ascontiguousarray(np.asarray(index, dtype=np.int32))
+    B, C, N = data.shape
+    out = np.zeros((B, C, K), dtype=np.int32)
+    scratch = np.zeros((B, C, K), dtype=np.float32)
+    rc = lib.index_max_oracle(_p(data, ctypes.c_float), _p(index, ctypes.c_int32), _p(out, ctypes.c_int32),
+                              ctypes.c_int64(B), ctypes.c_int64(C), ctypes.c_int64(N), ctypes.c_int64(K),
+                              _p(scratch, ctypes.c_float))
+    if rc != 0:
+        raise ValueError("index out of [0,K)")
+    return out
+
+
+def ball_query(dist, radius, K):
+    """Oracle for ball_query.forward_cuda_shared_mem (ball_query_cuda.cu:11-50)."""
+    lib = _lib("libops_oracle.so")
+    dist = np.ascontiguousarray(np.asarray(dist, dtype=np.float32))
+    B, M, N = dist.shape
+    out = np.zeros((B, M, K), dtype=np.int32)
+    lib.ball_query_oracle(_p(dist, ctypes.c_float), ctypes.c_float(float(radius)), _p(out, ctypes.c_int32),
+                          ctypes.c_int64(B), ctypes.c_int64(M), ctypes.c_int64(N), ctypes.c_int64(K))
+    return out
