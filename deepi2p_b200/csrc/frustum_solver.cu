@@ -1,0 +1,1065 @@
+// Batched robust bounded Levenberg-Marquardt solver for the inverse-camera-projection
+// ("frustum") registration problem, written for sm_100a.
+//
+// Replaces FrustumRegistration.solvePGivenK (evaluation/frustum_reg/src/registration.cpp:9-186)
+// and the multi-start loop around it (evaluation/registration_lsq.py:127-186).  One thread block
+// owns one (cloud, labels, intrinsics, init pose) problem from its first evaluation to its final
+// pose: point tiles are staged into shared memory with 1-D bulk copies (TMA engine) signalled on
+// mbarriers, every thread evaluates the per-point residual / Jacobian in fp64, the block reduces
+// cost, J^T r and J^T J in a fixed order, and thread 0 runs the trust-region control flow
+// (Jacobi scaling, LM damping, Cholesky of the damped normal matrix, model cost change, box
+// projection, projected Armijo line search with cubic interpolation, step acceptance and the
+// tolerance tests) without ever returning to the host.  A persistent grid pulls problems from an
+// atomic queue; a second tiny kernel takes the per-sample arg-min over inits and builds the 4x4.
+//
+// Residual definitions: registration_3d.hpp:34-68,105-127 / registration_2d.hpp:34-69,106-129.
+// Algorithm text: SURVEY.md Appendix A; oracle/frustum_oracle.cpp is the CPU checker.
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+
+#include "common.cuh"
+
+namespace dib {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr int kThreads = 128;           // threads per problem (CTA)
+constexpr int kWarps = kThreads / 32;
+constexpr int kTile = 1024;             // points per staged tile
+constexpr int kStages = 3;              // bulk-copy ring depth
+
+struct Cam {
+  double fx, fy, cx, cy, W1, H1, hW, hH;
+};
+
+// Per-evaluation pose constants, computed once by thread 0 and broadcast through shared memory.
+struct PoseConst {
+  double R[9];    // rotation applied to the point (first-order I + [a]x when |a|^2 <= DBL_EPSILON)
+  double t[3];
+  double Jl[9];   // 6-DoF: left Jacobian of SO(3); d(R p)/da = -[R p]x Jl
+  double cD, sD;  // 4-DoF: cos/sin used in d q / d ry
+  int small;      // first-order branch taken
+};
+
+template <int P>
+struct NAcc {
+  static constexpr int NA = P * (P + 1) / 2;
+  static constexpr int N = 1 + P + NA;   // cost, g, packed upper triangle of J^T J
+};
+
+__host__ __device__ constexpr int tri(int P, int j, int k) {   // j <= k
+  return j * P - j * (j - 1) / 2 + (k - j);
+}
+
+// ------------------------------------------------------------------------------------------
+// Pose constants.
+// ------------------------------------------------------------------------------------------
+template <int P>
+__device__ void make_pose(const double* x, PoseConst* pc) {
+  if (P == 4) {
+    const double ry = x[0];
+    pc->t[0] = x[1]; pc->t[1] = x[2]; pc->t[2] = x[3];
+    double c, s;
+    if (ry * ry > DBL_EPSILON) { sincos(ry, &s, &c); pc->cD = c; pc->sD = s; pc->small = 0; }
+    else { c = 1.0; s = ry; pc->cD = 1.0; pc->sD = 0.0; pc->small = 1; }
+    pc->R[0] = c; pc->R[1] = 0; pc->R[2] = s;
+    pc->R[3] = 0; pc->R[4] = 1; pc->R[5] = 0;
+    pc->R[6] = -s; pc->R[7] = 0; pc->R[8] = c;
+  } else {
+    const double ax = x[0], ay = x[1], az = x[2];
+    pc->t[0] = x[3]; pc->t[1] = x[4]; pc->t[2] = x[5];
+    const double th2 = ax * ax + ay * ay + az * az;
+    if (th2 > DBL_EPSILON) {
+      const double th = sqrt(th2);
+      double s, c;
+      sincos(th, &s, &c);
+      const double wx = ax / th, wy = ay / th, wz = az / th;
+      const double omc = 1.0 - c;
+      pc->R[0] = c + wx * wx * omc;      pc->R[1] = wx * wy * omc - wz * s; pc->R[2] = wy * s + wx * wz * omc;
+      pc->R[3] = wz * s + wx * wy * omc; pc->R[4] = c + wy * wy * omc;      pc->R[5] = -wx * s + wy * wz * omc;
+      pc->R[6] = -wy * s + wx * wz * omc; pc->R[7] = wx * s + wy * wz * omc; pc->R[8] = c + wz * wz * omc;
+      // Jl = I + A [a]x + B [a]x^2,  A = (1-cos)/th^2,  B = (th - sin)/th^3   (cancellation-free forms)
+      double sh, ch;
+      sincos(0.5 * th, &sh, &ch);
+      const double q = sh / (0.5 * th);
+      const double A = 0.5 * q * q;
+      double B;
+      if (th < 0.5) {
+        const double t2 = th2;
+        B = 1.0 / 6.0 + t2 * (-1.0 / 120.0 + t2 * (1.0 / 5040.0 + t2 * (-1.0 / 362880.0 +
+            t2 * (1.0 / 39916800.0 + t2 * (-1.0 / 6227020800.0 + t2 * (1.0 / 1307674368000.0))))));
+      } else {
+        B = (th - s) / (th2 * th);
+      }
+      // [a]x^2 = a a^T - th2 I
+      pc->Jl[0] = 1.0 + B * (ax * ax - th2); pc->Jl[1] = -A * az + B * ax * ay;     pc->Jl[2] = A * ay + B * ax * az;
+      pc->Jl[3] = A * az + B * ax * ay;      pc->Jl[4] = 1.0 + B * (ay * ay - th2); pc->Jl[5] = -A * ax + B * ay * az;
+      pc->Jl[6] = -A * ay + B * ax * az;     pc->Jl[7] = A * ax + B * ay * az;      pc->Jl[8] = 1.0 + B * (az * az - th2);
+      pc->small = 0;
+    } else {
+      pc->R[0] = 1;   pc->R[1] = -az; pc->R[2] = ay;
+      pc->R[3] = az;  pc->R[4] = 1;   pc->R[5] = -ax;
+      pc->R[6] = -ay; pc->R[7] = ax;  pc->R[8] = 1;
+      for (int i = 0; i < 9; ++i) pc->Jl[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      pc->small = 1;
+    }
+    pc->cD = 0; pc->sD = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-point evaluation.  acc = [cost, g[P], packed upper J^T J]; everything weighted by the
+// Cauchy corrector w = rho'(s) = 1/(1+s) (CauchyLoss(1.0), registration.cpp:103,121).
+// ------------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void rank1(double* acc, const double* J, double w, double r) {
+  const double wr = w * r;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    acc[1 + j] = fma(wr, J[j], acc[1 + j]);
+    const double wj = w * J[j];
+#pragma unroll
+    for (int k = j; k < P; ++k) acc[1 + P + tri(P, j, k)] = fma(wj, J[k], acc[1 + P + tri(P, j, k)]);
+  }
+}
+
+// Rows of the block Jacobian before robustification.  Returns the number of rows (1 or 3) and
+// fills r[] and J[][P]; inactive rows are exactly zero.
+template <int P>
+__device__ __forceinline__ bool point_rows(double px, double py, double pz, int lab, const Cam& cam,
+                                           const PoseConst& pc, double r[3], double J[3][P], int* nrows) {
+  constexpr int NR = P - 3;
+  const double rx = fma(pc.R[0], px, fma(pc.R[1], py, pc.R[2] * pz));
+  const double ry_ = fma(pc.R[3], px, fma(pc.R[4], py, pc.R[5] * pz));
+  const double rz = fma(pc.R[6], px, fma(pc.R[7], py, pc.R[8] * pz));
+  const double X = rx + pc.t[0], Y = ry_ + pc.t[1], Z = rz + pc.t[2];
+  const double iz = 1.0 / Z;
+  const double u = fma(cam.fx * X, iz, cam.cx);
+  const double v = fma(cam.fy * Y, iz, cam.cy);
+
+  bool any = false;
+  double su = 0.0, sv = 0.0, sz = 0.0;   // d r / d u, d r / d v, d r / d Z selectors per row
+  if (lab == 0) {
+    *nrows = 1;
+    const double du_ = u - cam.hW, dv_ = v - cam.hH;
+    const double xd = cam.hW - fabs(du_);
+    const double yd = cam.hH - fabs(dv_);
+    r[0] = 0.0;
+    if (Z > 0.0 && xd > 0.0 && yd > 0.0) {
+      r[0] = xd + yd;
+      su = (du_ < 0.0) ? 1.0 : -1.0;     // -sgn(u - W1/2), sgn(0) = +1
+      sv = (dv_ < 0.0) ? 1.0 : -1.0;
+      any = true;
+    }
+  } else {
+    *nrows = 3;
+    const double a0 = -u, b0 = u - cam.W1;
+    const double a1 = -v, b1 = v - cam.H1;
+    r[0] = (a0 < 0.0 ? 0.0 : a0) + (b0 < 0.0 ? 0.0 : b0);
+    r[1] = (a1 < 0.0 ? 0.0 : a1) + (b1 < 0.0 ? 0.0 : b1);
+    r[2] = (-Z < 0.0 ? 0.0 : -Z) * 100.0;
+    su = (a0 < 0.0 ? 0.0 : -1.0) + (b0 < 0.0 ? 0.0 : 1.0);
+    sv = (a1 < 0.0 ? 0.0 : -1.0) + (b1 < 0.0 ? 0.0 : 1.0);
+    sz = (-Z < 0.0) ? 0.0 : -100.0;
+    any = (su != 0.0) || (sv != 0.0) || (sz != 0.0);
+  }
+  if (!any) return false;
+
+  // d q / d rot (NR columns).
+  double dX[NR], dY[NR], dZ[NR];
+  if (P == 4) {
+    dX[0] = fma(-pc.sD, px, pc.cD * pz);
+    dY[0] = 0.0;
+    dZ[0] = -fma(pc.cD, px, pc.sD * pz);
+  } else {
+    const double a = pc.small ? px : rx, b = pc.small ? py : ry_, c = pc.small ? pz : rz;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      dX[k] = c * pc.Jl[3 + k] - b * pc.Jl[6 + k];
+      dY[k] = a * pc.Jl[6 + k] - c * pc.Jl[k];
+      dZ[k] = b * pc.Jl[k] - a * pc.Jl[3 + k];
+    }
+  }
+  const double au = cam.fx * iz, bu = (u - cam.cx) * iz;   // du = au dX - bu dZ
+  const double av = cam.fy * iz, bv = (v - cam.cy) * iz;   // dv = av dY - bv dZ
+  double dU[P], dV[P];
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    dU[k] = au * dX[k] - bu * dZ[k];
+    dV[k] = av * dY[k] - bv * dZ[k];
+  }
+  dU[NR] = au; dU[NR + 1] = 0.0; dU[NR + 2] = -bu;
+  dV[NR] = 0.0; dV[NR + 1] = av; dV[NR + 2] = -bv;
+  if (lab == 0) {
+#pragma unroll
+    for (int j = 0; j < P; ++j) J[0][j] = su * dU[j] + sv * dV[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < P; ++j) { J[0][j] = su * dU[j]; J[1][j] = sv * dV[j]; }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) J[2][k] = sz * dZ[k];
+    J[2][NR] = 0.0; J[2][NR + 1] = 0.0; J[2][NR + 2] = sz;
+  }
+  return true;
+}
+
+template <int P>
+__device__ __forceinline__ void point_accumulate(double px, double py, double pz, int lab, const Cam& cam,
+                                                 const PoseConst& pc, double* acc) {
+  double r[3], J[3][P];
+  int nrows;
+  if (!point_rows<P>(px, py, pz, lab, cam, pc, r, J, &nrows)) return;
+  if (lab == 0) {
+    const double s = r[0] * r[0];
+    const double sum = 1.0 + s;
+    const double w = 1.0 / sum;
+    acc[0] += 0.5 * log(sum);
+    rank1<P>(acc, J[0], w, r[0]);
+  } else {
+    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    const double sum = 1.0 + s;
+    const double w = 1.0 / sum;
+    acc[0] += 0.5 * log(sum);
+    // rows with a zero selector are exactly zero and contribute nothing
+    if (r[0] != 0.0 || J[0][P - 3] != 0.0) rank1<P>(acc, J[0], w, r[0]);
+    if (r[1] != 0.0 || J[1][P - 2] != 0.0) rank1<P>(acc, J[1], w, r[1]);
+    if (J[2][P - 1] != 0.0) rank1<P>(acc, J[2], w, r[2]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Shared-memory layout of one CTA.
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+struct alignas(16) TileBuf {
+  CT x[kTile];
+  CT y[kTile];
+  CT z[kTile];
+  int8_t lab[kTile];
+};
+
+struct LsSample {
+  double x, value, gradient;
+  int value_valid, gradient_valid;
+};
+
+template <int P>
+struct LMState {
+  static constexpr int NA = NAcc<P>::NA;
+  double x[P], x_norm, cost, g[P], A[NA], grad_max;
+  double scale[P], diag[P];
+  double radius, dec;
+  double step[P], delta[P], mcc;
+  double lb[P], ub[P];
+  double gd, dmax;
+  LsSample lower, prev, cur;
+  double xt[P];          // point of the pending evaluation
+  int reuse_diag, step_ok, invalid, iteration, max_iter;
+  int phase;             // 0 initial, 1 line-search sample, 2 candidate after failed line search
+  int ls_iter, evals, ls_steps, term;
+};
+
+template <typename CT, int P>
+struct Smem {
+  TileBuf<CT> tile[kStages];
+  alignas(8) uint64_t full[kStages];
+  double red[kWarps][NAcc<P>::N];
+  double tot[NAcc<P>::N];
+  PoseConst pose;
+  Cam cam;
+  LMState<P> lm;
+  int problem;       // current problem id (broadcast)
+  int go;            // 1 = another evaluation requested
+};
+
+// ------------------------------------------------------------------------------------------
+// One pass over a cloud: stages tiles, accumulates, block-reduces into sm.tot (all threads must
+// call).  `seq` is the CTA-lifetime count of consumed tiles (selects ring slot and phase).
+// ------------------------------------------------------------------------------------------
+template <typename CT>
+__device__ __forceinline__ void issue_tile(TileBuf<CT>* buf, uint64_t* bar, const CT* xyz_s, const int8_t* lab_s,
+                                           int n_stride, int n, int t) {
+  const int base = t * kTile;
+  int cnt = n - base;
+  if (cnt > kTile) cnt = kTile;
+  const int cnt16 = (cnt + 15) & ~15;
+  const uint32_t cb = cnt16 * sizeof(CT);
+  mbar_expect_tx(bar, 3 * cb + cnt16);
+  bulk_g2s(buf->x, xyz_s + base, cb, bar);
+  bulk_g2s(buf->y, xyz_s + n_stride + base, cb, bar);
+  bulk_g2s(buf->z, xyz_s + 2 * (size_t)n_stride + base, cb, bar);
+  bulk_g2s(buf->lab, lab_s + base, cnt16, bar);
+}
+
+template <typename CT, int P>
+__device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, int n_stride, int n,
+                               uint32_t& seq) {
+  constexpr int N = NAcc<P>::N;
+  const int tid = threadIdx.x;
+  const int ntiles = (n + kTile - 1) / kTile;
+  if (tid == 0) {
+    const int pre = ntiles < kStages ? ntiles : kStages;
+    for (int t = 0; t < pre; ++t) {
+      const uint32_t q = seq + t;
+      issue_tile<CT>(&sm.tile[q % kStages], &sm.full[q % kStages], xyz_s, lab_s, n_stride, n, t);
+    }
+  }
+  double acc[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) acc[j] = 0.0;
+  const Cam cam = sm.cam;
+  const PoseConst& pc = sm.pose;
+
+  for (int t = 0; t < ntiles; ++t) {
+    const uint32_t q = seq + t;
+    const int stage = q % kStages;
+    mbar_wait(&sm.full[stage], (q / kStages) & 1);
+    const TileBuf<CT>& tb = sm.tile[stage];
+    int cnt = n - t * kTile;
+    if (cnt > kTile) cnt = kTile;
+    for (int i = tid; i < cnt; i += kThreads) {
+      const int lab = tb.lab[i];
+      if (lab == 0 || lab == 1)
+        point_accumulate<P>((double)tb.x[i], (double)tb.y[i], (double)tb.z[i], lab, cam, pc, acc);
+    }
+    __syncthreads();   // every thread is done with this ring slot
+    if (tid == 0 && t + kStages < ntiles) {
+      const uint32_t qn = q + kStages;
+      issue_tile<CT>(&sm.tile[qn % kStages], &sm.full[qn % kStages], xyz_s, lab_s, n_stride, n, t + kStages);
+    }
+  }
+  seq += ntiles;
+
+  // fixed-order reduction: butterfly inside the warp, then warps 0..kWarps-1 in order
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    double v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    acc[j] = v;
+  }
+  const int warp = tid >> 5, lane = tid & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) sm.red[warp][j] = acc[j];
+  }
+  __syncthreads();
+  if (tid < N) {
+    double v = sm.red[0][tid];
+#pragma unroll
+    for (int w = 1; w < kWarps; ++w) v += sm.red[w][tid];
+    sm.tot[tid] = v;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// Trust-region control flow (thread 0 only).
+// ------------------------------------------------------------------------------------------
+template <int P>
+__device__ void project_plus(const LMState<P>& st, const double* x, const double* d, double a, double* out) {
+  for (int j = 0; j < P; ++j) {
+    double v = x[j] + a * d[j];
+    v = fmax(v, st.lb[j]);
+    v = fmin(v, st.ub[j]);
+    out[j] = v;
+  }
+}
+
+template <int P>
+__device__ double grad_max_norm(const LMState<P>& st, const double* x, const double* g) {
+  double mx = 0.0;
+  for (int j = 0; j < P; ++j) {
+    double v = x[j] - g[j];
+    v = fmax(v, st.lb[j]);
+    v = fmin(v, st.ub[j]);
+    mx = fmax(mx, fabs(x[j] - v));
+  }
+  return mx;
+}
+
+// Solve (As + diag(d2)) y = gs by Cholesky; As given as packed upper triangle.  false if not SPD.
+template <int P>
+__device__ bool chol_solve(const double* As, const double* d2, const double* gs, double* y) {
+  double L[P][P];
+  for (int j = 0; j < P; ++j) {
+    for (int i = j; i < P; ++i) {
+      double s = As[tri(P, j, i)] + (i == j ? d2[j] : 0.0);
+      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
+      if (i == j) {
+        if (!(s > 0.0)) return false;
+        L[j][j] = sqrt(s);
+      } else {
+        L[i][j] = s / L[j][j];
+      }
+    }
+  }
+  double z[P];
+  for (int i = 0; i < P; ++i) {
+    double s = gs[i];
+    for (int k = 0; k < i; ++k) s -= L[i][k] * z[k];
+    z[i] = s / L[i][i];
+  }
+  for (int i = P - 1; i >= 0; --i) {
+    double s = z[i];
+    for (int k = i + 1; k < P; ++k) s -= L[k][i] * y[k];
+    y[i] = s / L[i][i];
+  }
+  return true;
+}
+
+__device__ double poly_eval(const double* p, int n, double x) {   // n coefficients, highest first
+  double v = 0.0;
+  for (int i = 0; i < n; ++i) v = v * x + p[i];
+  return v;
+}
+
+__device__ double ipow(double x, int k) {
+  double v = 1.0;
+  for (int i = 0; i < k; ++i) v *= x;
+  return v;
+}
+
+// Real parts of all roots of p (n coefficients, highest first; n - 1 <= 4).
+__device__ int poly_roots_real(const double* pin, int n, double* roots) {
+  double p[6];
+  int lead = 0;
+  while (lead < n && pin[lead] == 0.0) ++lead;
+  const int m = n - lead;
+  for (int i = 0; i < m; ++i) p[i] = pin[lead + i];
+  const int deg = m - 1;
+  if (deg <= 0) return 0;
+  if (deg == 1) { roots[0] = -p[1] / p[0]; return 1; }
+  if (deg == 2) {
+    const double a = p[0], b = p[1], c = p[2];
+    const double D = b * b - 4 * a * c;
+    const double sD = sqrt(fabs(D));
+    if (D >= 0) {
+      if (b >= 0) { roots[0] = (-b - sD) / (2.0 * a); roots[1] = (2.0 * c) / (-b - sD); }
+      else { roots[0] = (2.0 * c) / (-b + sD); roots[1] = (-b + sD) / (2.0 * a); }
+    } else { roots[0] = -b / (2.0 * a); roots[1] = roots[0]; }
+    return 2;
+  }
+  // Durand-Kerner on the monic polynomial
+  double zr[5], zi[5], c[6];
+  double maxc = 0.0;
+  for (int i = 0; i <= deg; ++i) c[i] = p[i] / p[0];
+  for (int i = 1; i <= deg; ++i) maxc = fmax(maxc, fabs(c[i]));
+  const double radius = 1.0 + maxc;
+  for (int i = 0; i < deg; ++i) {
+    double s, co;
+    sincos(2.0 * 3.14159265358979323846 * i / deg + 0.4, &s, &co);
+    zr[i] = 0.5 * radius * co; zi[i] = 0.5 * radius * s;
+  }
+  for (int it = 0; it < 500; ++it) {
+    double change = 0.0;
+    for (int i = 0; i < deg; ++i) {
+      double nr = 0.0, ni = 0.0;
+      for (int k = 0; k <= deg; ++k) {
+        const double tr = nr * zr[i] - ni * zi[i] + c[k];
+        const double ti = nr * zi[i] + ni * zr[i];
+        nr = tr; ni = ti;
+      }
+      double dr = 1.0, di = 0.0;
+      for (int j = 0; j < deg; ++j) if (j != i) {
+        const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
+        const double tr = dr * er - di * ei, ti = dr * ei + di * er;
+        dr = tr; di = ti;
+      }
+      double den = dr * dr + di * di;
+      if (den == 0.0) { dr = 1e-300; di = 0.0; den = dr * dr; if (den == 0.0) den = 1e-300; }
+      const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
+      zr[i] -= qr; zi[i] -= qi;
+      change = fmax(change, sqrt(qr * qr + qi * qi));
+    }
+    if (change < 1e-15 * radius) break;
+  }
+  for (int i = 0; i < deg; ++i) roots[i] = zr[i];
+  return deg;
+}
+
+// Step size minimising the polynomial that interpolates the line-search samples over
+// [xmin, xmax] (cubic interpolation: values and gradients of lower / current / previous).
+__device__ double interpolating_min_step(const LsSample& lower, const LsSample& previous, const LsSample& current,
+                                         double xmin, double xmax) {
+  if (!current.value_valid) return fmin(fmax(current.x * 0.5, xmin), xmax);
+  const LsSample* s[3] = {&lower, &current, &previous};
+  const int ns = previous.value_valid ? 3 : 2;
+  int nc = 0;
+  for (int i = 0; i < ns; ++i) { if (s[i]->value_valid) ++nc; if (s[i]->gradient_valid) ++nc; }
+  const int deg = nc - 1;
+  double M[6][6], rhs[6], poly[6];
+  for (int i = 0; i < 6; ++i) { rhs[i] = 0; poly[i] = 0; for (int j = 0; j < 6; ++j) M[i][j] = 0; }
+  int row = 0;
+  for (int i = 0; i < ns; ++i) {
+    if (s[i]->value_valid) {
+      for (int j = 0; j <= deg; ++j) M[row][j] = ipow(s[i]->x, deg - j);
+      rhs[row] = s[i]->value; ++row;
+    }
+    if (s[i]->gradient_valid) {
+      for (int j = 0; j < deg; ++j) M[row][j] = (deg - j) * ipow(s[i]->x, deg - j - 1);
+      rhs[row] = s[i]->gradient; ++row;
+    }
+  }
+  // full-pivot elimination
+  int perm[6];
+  for (int i = 0; i < nc; ++i) perm[i] = i;
+  for (int k = 0; k < nc; ++k) {
+    int pr = k, pcv = k; double best = -1.0;
+    for (int i = k; i < nc; ++i) for (int j = k; j < nc; ++j)
+      if (fabs(M[i][j]) > best) { best = fabs(M[i][j]); pr = i; pcv = j; }
+    if (best == 0.0) { for (int i = k; i < nc; ++i) rhs[i] = 0.0; break; }
+    if (pr != k) { for (int j = 0; j < nc; ++j) { double t = M[pr][j]; M[pr][j] = M[k][j]; M[k][j] = t; } double t = rhs[pr]; rhs[pr] = rhs[k]; rhs[k] = t; }
+    if (pcv != k) { for (int i = 0; i < nc; ++i) { double t = M[i][pcv]; M[i][pcv] = M[i][k]; M[i][k] = t; } int t = perm[pcv]; perm[pcv] = perm[k]; perm[k] = t; }
+    for (int i = k + 1; i < nc; ++i) {
+      const double f = M[i][k] / M[k][k];
+      for (int j = k; j < nc; ++j) M[i][j] -= f * M[k][j];
+      rhs[i] -= f * rhs[k];
+    }
+  }
+  double z[6];
+  for (int k = nc - 1; k >= 0; --k) {
+    if (M[k][k] == 0.0) { z[k] = 0.0; continue; }
+    double sacc = rhs[k];
+    for (int j = k + 1; j < nc; ++j) sacc -= M[k][j] * z[j];
+    z[k] = sacc / M[k][k];
+  }
+  for (int k = 0; k < nc; ++k) poly[perm[k]] = z[k];
+
+  double best_x = (xmin + xmax) / 2.0;
+  double best_v = poly_eval(poly, nc, best_x);
+  const double vmin = poly_eval(poly, nc, xmin);
+  if (vmin < best_v) { best_v = vmin; best_x = xmin; }
+  const double vmax = poly_eval(poly, nc, xmax);
+  if (vmax < best_v) { best_v = vmax; best_x = xmax; }
+  if (nc <= 2) return best_x;
+  double der[6], roots[5];
+  for (int j = 0; j < deg; ++j) der[j] = (deg - j) * poly[j];
+  const int nr = poly_roots_real(der, deg, roots);
+  for (int i = 0; i < nr; ++i) {
+    if (roots[i] < xmin || roots[i] > xmax) continue;
+    const double v = poly_eval(poly, nc, roots[i]);
+    if (v < best_v) { best_v = v; best_x = roots[i]; }
+  }
+  return best_x;
+}
+
+enum { LM_DONE = 0, LM_EVAL = 1 };
+
+// Starts the next trust-region iteration(s) until an evaluation is needed or the solve ends.
+template <int P>
+__device__ int lm_next_step(LMState<P>& st) {
+  constexpr int NA = NAcc<P>::NA;
+  for (;;) {
+    if (st.iteration >= st.max_iter) { st.term = 3; return LM_DONE; }
+    if (st.step_ok && st.grad_max <= 1e-10) { st.term = 0; return LM_DONE; }
+    if (st.radius <= 1e-32) { st.term = 4; return LM_DONE; }
+    ++st.iteration;
+    st.step_ok = 0;
+
+    double As[NA], gs[P], d2[P], y[P];
+    for (int j = 0; j < P; ++j) {
+      gs[j] = st.g[j] * st.scale[j];
+      for (int k = j; k < P; ++k) As[tri(P, j, k)] = st.A[tri(P, j, k)] * st.scale[j] * st.scale[k];
+    }
+    if (!st.reuse_diag)
+      for (int j = 0; j < P; ++j) st.diag[j] = fmin(fmax(As[tri(P, j, j)], 1e-6), 1e32);
+    st.reuse_diag = 1;
+    for (int j = 0; j < P; ++j) { const double l = sqrt(st.diag[j] / st.radius); d2[j] = l * l; }
+    bool ok = chol_solve<P>(As, d2, gs, y);
+    double mcc = 0.0;
+    if (ok) {
+      // model cost change = -step^T gs - 1/2 step^T As step, step = -y
+      double quad = 0.0, lin = 0.0;
+      for (int j = 0; j < P; ++j) {
+        st.step[j] = -y[j];
+        if (!isfinite(st.step[j])) ok = false;
+      }
+      for (int j = 0; j < P; ++j) {
+        lin += st.step[j] * gs[j];
+        double rowsum = 0.0;
+        for (int k = 0; k < P; ++k) rowsum += As[j <= k ? tri(P, j, k) : tri(P, k, j)] * st.step[k];
+        quad += st.step[j] * rowsum;
+      }
+      mcc = -lin - 0.5 * quad;
+    }
+    if (!ok || !(mcc > 0.0)) {
+      if (++st.invalid >= 5) { st.term = 5; return LM_DONE; }
+      st.radius *= 0.5;
+      st.reuse_diag = 1;
+      continue;
+    }
+    st.invalid = 0;
+    st.mcc = mcc;
+    double gd = 0.0, dmax = 0.0;
+    for (int j = 0; j < P; ++j) {
+      st.delta[j] = st.step[j] * st.scale[j];
+      gd += st.g[j] * st.delta[j];
+      dmax = fmax(dmax, fabs(st.delta[j]));
+    }
+    st.gd = gd; st.dmax = dmax;
+    st.lower.x = 0.0; st.lower.value = st.cost; st.lower.gradient = gd; st.lower.value_valid = 1; st.lower.gradient_valid = 1;
+    st.prev.value_valid = 0; st.prev.gradient_valid = 0; st.prev.x = 0; st.prev.value = 0; st.prev.gradient = 0;
+    st.cur.x = 1.0;
+    st.ls_iter = 0;
+    project_plus<P>(st, st.x, st.delta, 1.0, st.xt);
+    st.phase = 1;
+    return LM_EVAL;
+  }
+}
+
+template <int P>
+__device__ int lm_after_candidate(LMState<P>& st, const double* tot) {
+  constexpr int NA = NAcc<P>::NA;
+  const double ccost = tot[0];
+  double sn = 0.0;
+  for (int j = 0; j < P; ++j) sn += (st.x[j] - st.xt[j]) * (st.x[j] - st.xt[j]);
+  if (sqrt(sn) <= 1e-8 * (st.x_norm + 1e-8)) { st.term = 1; return LM_DONE; }
+  if (fabs(st.cost - ccost) <= 1e-6 * st.cost) { st.term = 2; return LM_DONE; }
+  const double rho = (st.cost - ccost) / st.mcc;
+  if (rho > 1e-3) {
+    double xn = 0.0;
+    for (int j = 0; j < P; ++j) { st.x[j] = st.xt[j]; xn += st.x[j] * st.x[j]; st.g[j] = tot[1 + j]; }
+    st.x_norm = sqrt(xn);
+    st.cost = ccost;
+    for (int j = 0; j < NA; ++j) st.A[j] = tot[1 + P + j];
+    st.grad_max = grad_max_norm<P>(st, st.x, st.g);
+    const double t = 2.0 * rho - 1.0;
+    st.radius = st.radius / fmax(1.0 / 3.0, 1.0 - t * t * t);
+    st.radius = fmin(1e16, st.radius);
+    st.dec = 2.0;
+    st.reuse_diag = 0;
+    st.step_ok = 1;
+  } else {
+    st.radius = st.radius / st.dec;
+    st.dec *= 2.0;
+    st.reuse_diag = 1;
+  }
+  return lm_next_step<P>(st);
+}
+
+// Consumes the evaluation at st.xt (totals in tot).  Returns LM_EVAL with a new st.xt or LM_DONE.
+template <int P>
+__device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
+  constexpr int NA = NAcc<P>::NA;
+  ++st.evals;
+  if (st.phase == 0) {
+    st.cost = tot[0];
+    for (int j = 0; j < P; ++j) st.g[j] = tot[1 + j];
+    for (int j = 0; j < NA; ++j) st.A[j] = tot[1 + P + j];
+    for (int j = 0; j < P; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.A[tri(P, j, j)]));
+    st.grad_max = grad_max_norm<P>(st, st.x, st.g);
+    st.step_ok = 1;
+    return lm_next_step<P>(st);
+  }
+  if (st.phase == 1) {
+    LsSample& cur = st.cur;
+    cur.value = tot[0];
+    cur.value_valid = isfinite(cur.value) ? 1 : 0;
+    double gr = 0.0;
+    for (int j = 0; j < P; ++j) gr += st.delta[j] * tot[1 + j];
+    cur.gradient = gr;
+    cur.gradient_valid = (cur.value_valid && isfinite(gr)) ? 1 : 0;
+    const bool armijo_ok = cur.value_valid && !(cur.value > st.cost + 1e-4 * st.gd * cur.x);
+    if (armijo_ok) {
+      for (int j = 0; j < P; ++j) st.delta[j] *= cur.x;
+      return lm_after_candidate<P>(st, tot);      // candidate == this sample, bit for bit
+    }
+    ++st.ls_iter;
+    ++st.ls_steps;
+    bool fail = st.ls_iter >= 20;
+    double a = 0.0;
+    if (!fail) {
+      a = interpolating_min_step(st.lower, st.prev, cur, 1e-3 * cur.x, 0.6 * cur.x);
+      if (a * st.dmax < 1e-9) fail = true;
+    }
+    if (fail) {
+      // line search failed: the full step is the candidate (delta untouched)
+      project_plus<P>(st, st.x, st.delta, 1.0, st.xt);
+      st.phase = 2;
+      return LM_EVAL;
+    }
+    st.prev = cur;
+    cur.x = a;
+    {
+      double sd[P];
+      for (int j = 0; j < P; ++j) sd[j] = a * st.delta[j];
+      project_plus<P>(st, st.x, sd, 1.0, st.xt);
+    }
+    return LM_EVAL;
+  }
+  return lm_after_candidate<P>(st, tot);
+}
+
+// Returns LM_EVAL (st.xt set) or LM_DONE (infeasible start).
+template <int P>
+__device__ int lm_begin(LMState<P>& st, const double* init4, const double* lb3, const double* ub3, int max_iter) {
+  constexpr int toff = P - 3;
+  for (int j = 0; j < P; ++j) { st.lb[j] = -DBL_MAX; st.ub[j] = DBL_MAX; st.x[j] = 0.0; }
+  for (int k = 0; k < 3; ++k) { st.lb[toff + k] = lb3[k]; st.ub[toff + k] = ub3[k]; st.x[toff + k] = init4[1 + k]; }
+  st.x[P == 4 ? 0 : 1] = init4[0];        // registration.cpp:34-50
+  st.max_iter = max_iter;
+  st.iteration = 0; st.evals = 0; st.ls_steps = 0; st.term = -1; st.invalid = 0;
+  st.radius = 1e4; st.dec = 2.0; st.reuse_diag = 0; st.step_ok = 1; st.phase = 0;
+  st.cost = 0.0; st.grad_max = 0.0;
+  for (int j = 0; j < P; ++j) st.g[j] = 0.0;
+  for (int j = 0; j < P; ++j)
+    if (st.x[j] < st.lb[j] || st.x[j] > st.ub[j]) { st.term = 6; return LM_DONE; }
+  double xn = 0.0;
+  for (int j = 0; j < P; ++j) { st.xt[j] = st.x[j]; xn += st.x[j] * st.x[j]; }
+  st.x_norm = sqrt(xn);
+  return LM_EVAL;
+}
+
+__device__ void make_cam(const double* K9, double H, double W, Cam* cam) {
+  cam->fx = K9[0]; cam->fy = K9[4]; cam->cx = K9[2]; cam->cy = K9[5];   // registration.cpp:79-82
+  cam->W1 = W - 1.0; cam->H1 = H - 1.0;                                 // registration.cpp:21-22
+  cam->hW = cam->W1 * 0.5; cam->hH = cam->H1 * 0.5;
+}
+
+struct SolveArgs {
+  const void* xyz;
+  const int8_t* label;
+  const int32_t* n_pts;
+  int n_stride;
+  const double* K9;
+  const double* init;
+  double lb[3], ub[3];
+  double H, W;
+  int max_iter, S, I;
+  double* params_all;   // [S*I*6]
+  double* cost_all;     // [S*I]
+  int32_t* stats_all;   // [S*I*4]
+  unsigned int* queue;  // problem counter
+};
+
+template <typename CT, int P>
+__global__ void __launch_bounds__(kThreads) frustum_solve_kernel(SolveArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t seq = 0;
+  const int total = a.S * a.I;
+
+  for (;;) {
+    if (tid == 0) sm.problem = (int)atomicAdd(a.queue, 1u);
+    __syncthreads();
+    const int prob = sm.problem;
+    if (prob >= total) break;
+    const int s = prob / a.I;
+    const CT* xyz_s = reinterpret_cast<const CT*>(a.xyz) + (size_t)s * 3 * a.n_stride;
+    const int8_t* lab_s = a.label + (size_t)s * a.n_stride;
+    const int n = a.n_pts ? a.n_pts[s] : a.n_stride;
+    if (tid == 0) {
+      make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &sm.cam);
+      const int rc = lm_begin<P>(sm.lm, a.init + (size_t)prob * 4, a.lb, a.ub, a.max_iter);
+      sm.go = rc;
+      if (rc == LM_EVAL) make_pose<P>(sm.lm.xt, &sm.pose);
+    }
+    __syncthreads();
+    while (sm.go == LM_EVAL) {
+      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, a.n_stride, n, seq);
+      if (tid == 0) {
+        const int rc = lm_consume<P>(sm.lm, sm.tot);
+        sm.go = rc;
+        if (rc == LM_EVAL) make_pose<P>(sm.lm.xt, &sm.pose);
+      }
+      __syncthreads();
+    }
+    if (tid == 0) {
+      const LMState<P>& st = sm.lm;
+      double* po = a.params_all + (size_t)prob * 6;
+      for (int j = 0; j < 6; ++j) po[j] = (j < P) ? st.x[j] : 0.0;
+      a.cost_all[prob] = st.cost;
+      int32_t* so = a.stats_all + (size_t)prob * 4;
+      so[0] = st.iteration; so[1] = st.evals; so[2] = st.ls_steps; so[3] = st.term;
+    }
+    __syncthreads();
+  }
+}
+
+// Pose matrix from parameters (registration.cpp:161-185).
+__device__ void pose_matrix(const double* x, int P, double* M) {
+  double aa[3];
+  const double* t;
+  if (P == 4) { aa[0] = 0; aa[1] = x[0]; aa[2] = 0; t = x + 1; } else { aa[0] = x[0]; aa[1] = x[1]; aa[2] = x[2]; t = x + 3; }
+  double R[9];
+  const double th2 = aa[0] * aa[0] + aa[1] * aa[1] + aa[2] * aa[2];
+  if (th2 > DBL_EPSILON) {
+    const double th = sqrt(th2);
+    const double wx = aa[0] / th, wy = aa[1] / th, wz = aa[2] / th;
+    double s, c;
+    sincos(th, &s, &c);
+    const double omc = 1.0 - c;
+    R[0] = c + wx * wx * omc;       R[1] = wx * wy * omc - wz * s;  R[2] = wy * s + wx * wz * omc;
+    R[3] = wz * s + wx * wy * omc;  R[4] = c + wy * wy * omc;       R[5] = -wx * s + wy * wz * omc;
+    R[6] = -wy * s + wx * wz * omc; R[7] = wx * s + wy * wz * omc;  R[8] = c + wz * wz * omc;
+  } else {
+    R[0] = 1; R[1] = -aa[2]; R[2] = aa[1];
+    R[3] = aa[2]; R[4] = 1; R[5] = -aa[0];
+    R[6] = -aa[1]; R[7] = aa[0]; R[8] = 1;
+  }
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) M[4 * i + j] = R[3 * i + j]; M[4 * i + 3] = t[i]; }
+  M[12] = 0; M[13] = 0; M[14] = 0; M[15] = 1;
+}
+
+// Per-sample arg-min over inits (lowest index wins ties; NaN never wins) + pose matrix.
+__global__ void frustum_finalize_kernel(const double* params_all, const double* cost_all, int S, int I, int P,
+                                        double* P16_out, double* cost_out, int32_t* best_out) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  int best = 0;
+  double bc = cost_all[(size_t)s * I];
+  if (!(bc == bc)) bc = INFINITY;
+  for (int i = 1; i < I; ++i) {
+    const double c = cost_all[(size_t)s * I + i];
+    if (c < bc) { bc = c; best = i; }
+  }
+  pose_matrix(params_all + ((size_t)s * I + best) * 6, P, P16_out + (size_t)s * 16);
+  cost_out[s] = cost_all[(size_t)s * I + best];
+  if (best_out) best_out[s] = best;
+}
+
+template <typename CT, int P>
+__global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xyz, const int8_t* label,
+                                                                     const int32_t* n_pts, int n_stride,
+                                                                     const double* K9, const double* x, double H,
+                                                                     double W, double* cost_out, double* grad_out,
+                                                                     double* JtJ_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
+  const int tid = threadIdx.x;
+  const int s = blockIdx.x;
+  if (tid == 0) {
+    for (int k = 0; k < kStages; ++k) mbar_init(&sm.full[k], 1);
+    mbar_fence_init();
+    make_cam(K9 + (size_t)s * 9, H, W, &sm.cam);
+    make_pose<P>(x + (size_t)s * 6, &sm.pose);
+  }
+  __syncthreads();
+  uint32_t seq = 0;
+  const int n = n_pts ? n_pts[s] : n_stride;
+  evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride, n_stride, n, seq);
+  if (tid == 0) {
+    cost_out[s] = sm.tot[0];
+    for (int j = 0; j < 6; ++j) grad_out[(size_t)s * 6 + j] = (j < P) ? sm.tot[1 + j] : 0.0;
+    for (int j = 0; j < 36; ++j) JtJ_out[(size_t)s * 36 + j] = 0.0;
+    for (int j = 0; j < P; ++j)
+      for (int k = 0; k < P; ++k)
+        JtJ_out[(size_t)s * 36 + j * P + k] = sm.tot[1 + P + (j <= k ? tri(P, j, k) : tri(P, k, j))];
+  }
+}
+
+template <typename CT, int P>
+__global__ void frustum_residuals_kernel(const CT* xyz, const int8_t* label, int n, int n_stride, const double* K9,
+                                         const double* x, double H, double W, const int32_t* row_offset,
+                                         double* residuals) {
+  __shared__ PoseConst pc;
+  __shared__ Cam cam;
+  if (threadIdx.x == 0) { make_cam(K9, H, W, &cam); make_pose<P>(x, &pc); }
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int lab = label[i];
+  if (lab != 0 && lab != 1) return;
+  double r[3] = {0, 0, 0}, J[3][P];
+  int nrows = (lab == 1) ? 3 : 1;
+  const bool any = point_rows<P>((double)xyz[i], (double)xyz[n_stride + i], (double)xyz[2 * (size_t)n_stride + i], lab,
+                                 cam, pc, r, J, &nrows);
+  double s = 0.0;
+  for (int k = 0; k < nrows; ++k) s += r[k] * r[k];
+  const double sq = sqrt(1.0 / (1.0 + s));
+  const int ro = row_offset[i];
+  for (int k = 0; k < nrows; ++k) residuals[ro + k] = any ? r[k] * sq : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side of the C ABI.
+// ------------------------------------------------------------------------------------------
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+template <typename CT>
+static int check_cloud_args(const CT* xyz, const int8_t* label, int n_stride, int S) {
+  DIB_REQUIRE(xyz != nullptr && label != nullptr, "xyz/label must not be NULL");
+  DIB_REQUIRE(S >= 0 && n_stride >= 0, "negative size");
+  DIB_REQUIRE(n_stride % 16 == 0, "n_stride (%d) must be a multiple of 16", n_stride);
+  DIB_REQUIRE(((uintptr_t)xyz % 16) == 0 && ((uintptr_t)label % 16) == 0, "xyz/label must be 16-byte aligned");
+  return DIB_OK;
+}
+
+template <typename CT, int P>
+static int launch_solve(const SolveArgs& a, cudaStream_t st) {
+  auto kern = frustum_solve_kernel<CT, P>;
+  const size_t smem = sizeof(Smem<CT, P>);
+  DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, per_sm = 0;
+  DIB_CHECK_CUDA(cudaGetDevice(&dev));
+  DIB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  DIB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)sms * per_sm;
+  const long long total = (long long)a.S * a.I;
+  if (grid > total) grid = total;
+  if (grid < 1) return DIB_OK;
+  kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+template <typename CT>
+static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
+                       const double* init, const double* lb3, const double* ub3, double H, double W, int max_iter,
+                       int is_2d, int S, int I, double* P16_out, double* cost_out, int32_t* best_out,
+                       double* params_all, double* cost_all, int32_t* stats_all, void* workspace,
+                       size_t workspace_bytes, dib_stream_t stream) {
+  int rc = check_cloud_args<CT>(xyz, label, n_stride, S);
+  if (rc != DIB_OK) return rc;
+  DIB_REQUIRE(I >= 1, "I must be >= 1");
+  DIB_REQUIRE(K9 && init && lb3 && ub3 && P16_out && cost_out, "NULL argument");
+  DIB_REQUIRE((long long)S * I < (1ll << 31), "S*I too large");
+  if (S == 0) return DIB_OK;
+  if (workspace_bytes < frustum_solve_workspace_bytes(S, I) || workspace == nullptr) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, frustum_solve_workspace_bytes(S, I));
+    return DIB_ENOMEM;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned char* ws = (unsigned char*)workspace;
+  const size_t n = (size_t)S * I;
+  SolveArgs a;
+  a.queue = (unsigned int*)ws;
+  size_t off = 256;
+  a.params_all = params_all ? params_all : (double*)(ws + off);
+  off += align_up(n * 6 * sizeof(double), 256);
+  a.cost_all = cost_all ? cost_all : (double*)(ws + off);
+  off += align_up(n * sizeof(double), 256);
+  a.stats_all = stats_all ? stats_all : (int32_t*)(ws + off);
+  a.xyz = xyz; a.label = label; a.n_pts = n_pts; a.n_stride = n_stride; a.K9 = K9; a.init = init;
+  for (int k = 0; k < 3; ++k) { a.lb[k] = lb3[k]; a.ub[k] = ub3[k]; }
+  a.H = H; a.W = W; a.max_iter = max_iter; a.S = S; a.I = I;
+  DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
+  rc = is_2d ? launch_solve<CT, 4>(a, st) : launch_solve<CT, 6>(a, st);
+  if (rc != DIB_OK) return rc;
+  frustum_finalize_kernel<<<(S + 127) / 128, 128, 0, st>>>(a.params_all, a.cost_all, S, I, is_2d ? 4 : 6, P16_out,
+                                                          cost_out, best_out);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+template <typename CT>
+static int evaluate_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
+                          const double* x, double H, double W, int is_2d, int S, double* cost_out, double* grad_out,
+                          double* JtJ_out, dib_stream_t stream) {
+  int rc = check_cloud_args<CT>(xyz, label, n_stride, S);
+  if (rc != DIB_OK) return rc;
+  DIB_REQUIRE(K9 && x && cost_out && grad_out && JtJ_out, "NULL argument");
+  if (S == 0) return DIB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (is_2d) {
+    auto kern = frustum_evaluate_kernel<CT, 4>;
+    const size_t smem = sizeof(Smem<CT, 4>);
+    DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, cost_out, grad_out, JtJ_out);
+  } else {
+    auto kern = frustum_evaluate_kernel<CT, 6>;
+    const size_t smem = sizeof(Smem<CT, 6>);
+    DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, cost_out, grad_out, JtJ_out);
+  }
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+template <typename CT>
+static int residuals_single(const CT* xyz, const int8_t* label, int n, int n_stride, const double* K9,
+                            const double* x, double H, double W, int is_2d, const int32_t* row_offset,
+                            double* residuals, dib_stream_t stream) {
+  DIB_REQUIRE(xyz && label && K9 && x && row_offset && residuals, "NULL argument");
+  DIB_REQUIRE(n >= 0 && n <= n_stride, "bad n");
+  if (n == 0) return DIB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = (n + 255) / 256;
+  if (is_2d)
+    frustum_residuals_kernel<CT, 4><<<blocks, 256, 0, st>>>(xyz, label, n, n_stride, K9, x, H, W, row_offset, residuals);
+  else
+    frustum_residuals_kernel<CT, 6><<<blocks, 256, 0, st>>>(xyz, label, n, n_stride, K9, x, H, W, row_offset, residuals);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+}  // namespace dib
+
+extern "C" {
+
+int dib_abi_version(void) { return 1; }
+const char* dib_last_error(void) { return dib::g_err; }
+
+int dib_device_sm_count(void) {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return DIB_ENODEV;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return DIB_ENODEV;
+  return sms;
+}
+
+size_t frustum_solve_workspace_bytes(int S, int I) {
+  const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
+  return 256 + dib::align_up(n * 6 * sizeof(double), 256) + dib::align_up(n * sizeof(double), 256) +
+         dib::align_up(n * 4 * sizeof(int32_t), 256);
+}
+
+int frustum_solve_batch_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                            const double* K9, const double* init, const double* lb3, const double* ub3, double H,
+                            double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
+                            int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
+                            void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+  return dib::solve_batch<float>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
+                                 P16_out, cost_out, best_out, params_all, cost_all, stats_all, workspace,
+                                 workspace_bytes, stream);
+}
+
+int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                            const double* K9, const double* init, const double* lb3, const double* ub3, double H,
+                            double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
+                            int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
+                            void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+  return dib::solve_batch<double>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
+                                  P16_out, cost_out, best_out, params_all, cost_all, stats_all, workspace,
+                                  workspace_bytes, stream);
+}
+
+int frustum_evaluate_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
+                         const double* x, double H, double W, int is_2d, int S, double* cost_out, double* grad_out,
+                         double* JtJ_out, dib_stream_t stream) {
+  return dib::evaluate_batch<float>(xyz, label, n_pts, n_stride, K9, x, H, W, is_2d, S, cost_out, grad_out, JtJ_out,
+                                    stream);
+}
+int frustum_evaluate_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                         const double* K9, const double* x, double H, double W, int is_2d, int S, double* cost_out,
+                         double* grad_out, double* JtJ_out, dib_stream_t stream) {
+  return dib::evaluate_batch<double>(xyz, label, n_pts, n_stride, K9, x, H, W, is_2d, S, cost_out, grad_out, JtJ_out,
+                                     stream);
+}
+
+int frustum_residuals_f32(const float* xyz, const int8_t* label, int n, int n_stride, const double* K9,
+                          const double* x, double H, double W, int is_2d, const int32_t* row_offset,
+                          double* residuals, dib_stream_t stream) {
+  return dib::residuals_single<float>(xyz, label, n, n_stride, K9, x, H, W, is_2d, row_offset, residuals, stream);
+}
+int frustum_residuals_f64(const double* xyz, const int8_t* label, int n, int n_stride, const double* K9,
+                          const double* x, double H, double W, int is_2d, const int32_t* row_offset,
+                          double* residuals, dib_stream_t stream) {
+  return dib::residuals_single<double>(xyz, label, n, n_stride, K9, x, H, W, is_2d, row_offset, residuals, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,177 @@
+// index_max (segmented arg-max) and ball_query (first-K-within-radius) for sm_100a.
+//
+// index_max replaces models/index_max_ext/index_max_cuda.cu:30-62 (one thread per (b,c) scanning
+// N floats with stride C*N between neighbouring threads).  Here a CTA owns (b, a group of
+// channels): the cluster-id row index[b,:] is loaded once per group, data rows are streamed with
+// coalesced 128-bit loads, and the per-segment winner is kept in shared memory as a 64-bit key
+// (order-preserving float bits << 32 | ~n) under atomicMax -- max over a total order is
+// independent of arrival order, so the result is deterministic and equals the reference's
+// "strict > in ascending n" scan: largest value, lowest n on ties, values <= -1000 and NaN never
+// win, untouched segments stay 0.
+//
+// ball_query replaces models/ball_query_ext/ball_query_cuda.cu:11-50 (one thread per (b,m) row).
+// Here a warp owns a row: coalesced loads, ballot + popc ordered compaction, early exit once K
+// hits are found, then the reference's padding rule (none -> 0, fewer -> cyclic repeat).
+#include "common.cuh"
+
+namespace dib {
+
+constexpr int kImThreads = 256;
+
+__device__ __forceinline__ uint32_t ordered_bits(float v) {
+  const uint32_t b = __float_as_uint(v + 0.0f);   // -0 -> +0 so that -0 == +0 as in float compare
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+template <int CPB>
+__device__ __forceinline__ void im_consider(uint32_t* bestv, unsigned long long* bestk, int K, int c, int k,
+                                            float v, uint32_t n) {
+  if (!(v > -1000.0f)) return;                    // also rejects NaN
+  const uint32_t ord = ordered_bits(v);
+  uint32_t* pv = bestv + c * K + k;
+  if (ord >= *pv) {
+    atomicMax(pv, ord);
+    atomicMax(bestk + c * K + k, ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - n));
+  }
+}
+
+// grid = (ceil(C / CPB), B); dynamic smem = CPB * K * 12 bytes
+template <int CPB, bool VEC>
+__global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __restrict__ data,
+                                                               const int32_t* __restrict__ index,
+                                                               int32_t* __restrict__ out, int B, int C, int N, int K) {
+  extern __shared__ __align__(16) unsigned char im_smem[];
+  unsigned long long* bestk = reinterpret_cast<unsigned long long*>(im_smem);
+  uint32_t* bestv = reinterpret_cast<uint32_t*>(bestk + (size_t)CPB * K);
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * CPB;
+  const int nc = min(CPB, C - c0);
+  for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = 0u; }
+  __syncthreads();
+  const int32_t* idx = index + (size_t)b * N;
+  const float* rows = data + ((size_t)b * C + c0) * N;
+
+  if (VEC) {
+    const int n4 = N >> 2;
+    for (int i = threadIdx.x; i < n4; i += kImThreads) {
+      const int4 kk = __ldg(reinterpret_cast<const int4*>(idx) + i);
+      float4 vv[CPB];
+#pragma unroll
+      for (int c = 0; c < CPB; ++c)
+        if (c < nc) vv[c] = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)c * N) + i);
+      const uint32_t n = (uint32_t)i << 2;
+#pragma unroll
+      for (int c = 0; c < CPB; ++c) {
+        if (c < nc) {
+          if ((unsigned)kk.x < (unsigned)K) im_consider<CPB>(bestv, bestk, K, c, kk.x, vv[c].x, n);
+          if ((unsigned)kk.y < (unsigned)K) im_consider<CPB>(bestv, bestk, K, c, kk.y, vv[c].y, n + 1);
+          if ((unsigned)kk.z < (unsigned)K) im_consider<CPB>(bestv, bestk, K, c, kk.z, vv[c].z, n + 2);
+          if ((unsigned)kk.w < (unsigned)K) im_consider<CPB>(bestv, bestk, K, c, kk.w, vv[c].w, n + 3);
+        }
+      }
+    }
+  } else {
+    for (int i = threadIdx.x; i < N; i += kImThreads) {
+      const int k = __ldg(idx + i);
+      if ((unsigned)k >= (unsigned)K) continue;
+#pragma unroll
+      for (int c = 0; c < CPB; ++c)
+        if (c < nc) im_consider<CPB>(bestv, bestk, K, c, k, __ldcs(rows + (size_t)c * N + i), (uint32_t)i);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc * K; i += kImThreads) {
+    const unsigned long long key = bestk[i];
+    out[((size_t)b * C + c0) * K + i] = key ? (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)) : 0;
+  }
+}
+
+constexpr int kBqWarps = 8;
+constexpr int kBqUnroll = 16;
+
+// One warp per (b,m) row.
+__global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* __restrict__ dist, float radius,
+                                                                   int32_t* __restrict__ out, long long rows, int N,
+                                                                   int K) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * kBqWarps + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* d = dist + (size_t)row * N;
+  int32_t* o = out + (size_t)row * K;
+  int cnt = 0;
+  for (int base = 0; base < N && cnt < K; base += 32 * kBqUnroll) {
+    float v[kBqUnroll];
+#pragma unroll
+    for (int j = 0; j < kBqUnroll; ++j) {
+      const int n = base + j * 32 + lane;
+      v[j] = (n < N) ? __ldcs(d + n) : __int_as_float(0x7fc00000);   // NaN never hits
+    }
+#pragma unroll
+    for (int j = 0; j < kBqUnroll; ++j) {
+      const bool hit = v[j] <= radius;
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pos < K) o[pos] = base + j * 32 + lane;
+      }
+      cnt += __popc(m);
+    }
+  }
+  __syncwarp();
+  if (cnt == 0) {
+    for (int i = lane; i < K; i += 32) o[i] = 0;
+  } else if (cnt < K) {
+    for (int i = lane; i < K - cnt; i += 32) o[cnt + i] = o[i % cnt];   // sources are all < cnt: never overwritten
+  }
+}
+
+}  // namespace dib
+
+extern "C" {
+
+int index_max_forward(const float* data, const int32_t* index, int32_t* out, int B, int C, int N, int K,
+                      dib_stream_t stream) {
+  using namespace dib;
+  DIB_REQUIRE(data && index && out, "NULL argument");
+  DIB_REQUIRE(B >= 0 && C >= 0 && N >= 0 && K >= 1, "bad shape B=%d C=%d N=%d K=%d", B, C, N, K);
+  DIB_REQUIRE(B <= 65535, "B too large for grid.y");
+  if (B == 0 || C == 0) return DIB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool vec = (N % 4 == 0) && ((uintptr_t)data % 16 == 0) && ((uintptr_t)index % 16 == 0);
+  const size_t per_c = (size_t)K * 12;
+  const size_t limit = 200 * 1024;
+  int cpb = 4;
+  while (cpb > 1 && per_c * cpb > limit) cpb >>= 1;
+  DIB_REQUIRE(per_c * cpb <= limit, "K=%d too large for the shared-memory segment table", K);
+  const size_t smem = per_c * cpb;
+  dim3 grid((C + cpb - 1) / cpb, B);
+#define DIB_IM_LAUNCH(CPB, VEC)                                                                              \
+  do {                                                                                                       \
+    auto kern = dib::index_max_kernel<CPB, VEC>;                                                             \
+    DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    kern<<<grid, dib::kImThreads, smem, st>>>(data, index, out, B, C, N, K);                                 \
+  } while (0)
+  if (cpb == 4) { if (vec) DIB_IM_LAUNCH(4, true); else DIB_IM_LAUNCH(4, false); }
+  else if (cpb == 2) { if (vec) DIB_IM_LAUNCH(2, true); else DIB_IM_LAUNCH(2, false); }
+  else { if (vec) DIB_IM_LAUNCH(1, true); else DIB_IM_LAUNCH(1, false); }
+#undef DIB_IM_LAUNCH
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+int ball_query_forward(const float* dist, float radius, int32_t* out, int B, int M, int N, int K,
+                       dib_stream_t stream) {
+  using namespace dib;
+  DIB_REQUIRE(dist && out, "NULL argument");
+  DIB_REQUIRE(B >= 0 && M >= 0 && N >= 0 && K >= 1, "bad shape B=%d M=%d N=%d K=%d", B, M, N, K);
+  const long long rows = (long long)B * M;
+  if (rows == 0) return DIB_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long blocks = (rows + kBqWarps - 1) / kBqWarps;
+  DIB_REQUIRE(blocks < (1ll << 31), "too many rows");
+  ball_query_kernel<<<(unsigned)blocks, kBqWarps * 32, 0, st>>>(dist, radius, out, rows, N, K);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// On-device front end of the multi-start driver: get_initial_guess (evaluation/registration_lsq.py:196-220)
+// and the random perturbed inits (registration_lsq.py:163-164), so that a batch goes from
+// (cloud, predicted labels) to solver inputs without a host round-trip.
+//
+// Per sample (one CTA): mean of the predicted-inside points -> init_y_angle =
+// wrap_pi(atan2(mean_z, mean_x) - pi/2); zmin = min over predicted-inside points of the rotated z;
+// keep points with rotated z > zmin - 10, order-preserving compaction into the solver's
+// device record (xyz f32 SoA + int8 label, tail padded with ignored points); inits
+// ry_i = init_y_angle + N(0, sigma), t_i = (0, 0, U(-amp, amp)) from a counter-based Philox4x32-10
+// keyed by (seed; sample, init) so that a CPU restatement can reproduce them.
+// The reference draws from Python's unseeded `random`, so only the distribution can be matched.
+#include <cfloat>
+#include <cmath>
+
+#include "common.cuh"
+
+namespace dib {
+
+constexpr int kPrepThreads = 256;
+constexpr int kPrepWarps = kPrepThreads / 32;
+constexpr double kPi = 3.14159265358979323846;
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+__device__ double block_sum(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = scratch[0];
+  for (int w = 1; w < kPrepWarps; ++w) t += scratch[w];
+  return t;
+}
+
+__device__ double block_min(double v, double* scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = scratch[0];
+  for (int w = 1; w < kPrepWarps; ++w) t = fmin(t, scratch[w]);
+  return t;
+}
+
+// grid = S.  xyz_in [S][3][n_in_stride] f32, pred [S][n_in_stride] int8, n_in points valid.
+__global__ void __launch_bounds__(kPrepThreads)
+    frustum_prepare_kernel(const float* __restrict__ xyz_in, const int8_t* __restrict__ pred, int n_in,
+                           int n_in_stride, int n_out_stride, int I, unsigned long long seed, double ry_sigma,
+                           double t_amp, float* __restrict__ xyz_out, int8_t* __restrict__ label_out,
+                           int32_t* __restrict__ n_pts, double* __restrict__ init, double* __restrict__ init_y_angle,
+                           int32_t* __restrict__ degenerate) {
+  __shared__ double scratch[kPrepWarps];
+  __shared__ int warp_cnt[kPrepWarps];
+  __shared__ int s_base;
+  const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* px = xyz_in + (size_t)s * 3 * n_in_stride;
+  const float* py = px + n_in_stride;
+  const float* pz = py + n_in_stride;
+  const int8_t* lab = pred + (size_t)s * n_in_stride;
+
+  // pass 1: mean of predicted-inside points (fixed reduction order)
+  double sx = 0, sy = 0, sz = 0, cnt = 0;
+  for (int i = tid; i < n_in; i += kPrepThreads)
+    if (lab[i] == 1) { sx += (double)px[i]; sy += (double)py[i]; sz += (double)pz[i]; cnt += 1.0; }
+  sx = block_sum(sx, scratch); sz = block_sum(sz, scratch); cnt = block_sum(cnt, scratch);
+  (void)sy;
+  const bool degen = !(cnt > 0.0);
+  double ang = 0.0;
+  if (!degen) {
+    double a = atan2(sz / cnt, sx / cnt) - 0.5 * kPi;    // registration_lsq.py:203-207
+    a = fmod(a + kPi, 2.0 * kPi);                          // wrap_in_pi, :189-193
+    if (a < 0) a += 2.0 * kPi;
+    ang = a - kPi;
+  }
+  double sn, cs;
+  sincos(ang, &sn, &cs);
+
+  // pass 2: min rotated z over predicted-inside points (:209-212)
+  double zmin = DBL_MAX;
+  for (int i = tid; i < n_in; i += kPrepThreads)
+    if (lab[i] == 1) zmin = fmin(zmin, -sn * (double)px[i] + cs * (double)pz[i]);
+  zmin = block_min(zmin, scratch);
+  const double thresh = zmin - 10.0;
+
+  // pass 3: order-preserving compaction of the front points (:213-215)
+  float* ox = xyz_out + (size_t)s * 3 * n_out_stride;
+  float* oy = ox + n_out_stride;
+  float* oz = oy + n_out_stride;
+  int8_t* ol = label_out + (size_t)s * n_out_stride;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int start = 0; start < n_in; start += kPrepThreads) {
+    const int i = start + tid;
+    bool keep = false;
+    float x = 0, y = 0, z = 0;
+    int8_t l = -1;
+    if (i < n_in) {
+      x = px[i]; y = py[i]; z = pz[i]; l = lab[i];
+      keep = degen ? true : ((-sn * (double)x + cs * (double)z) > thresh);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+    if (keep) {
+      const int o = off + __popc(m & ((1u << lane) - 1u));
+      if (o < n_out_stride) { ox[o] = x; oy[o] = y; oz[o] = z; ol[o] = (l == 0 || l == 1) ? l : (int8_t)-1; }
+    }
+    __syncthreads();
+    if (tid == 0) { int t = 0; for (int w = 0; w < kPrepWarps; ++w) t += warp_cnt[w]; s_base += t; }
+    __syncthreads();
+  }
+  const int n_front = min(s_base, n_out_stride);
+  for (int i = n_front + tid; i < n_out_stride; i += kPrepThreads) { ox[i] = 0.f; oy[i] = 0.f; oz[i] = 0.f; ol[i] = -1; }
+  if (tid == 0) {
+    n_pts[s] = n_front;
+    init_y_angle[s] = ang;
+    degenerate[s] = degen ? 1 : 0;
+  }
+  // inits (:163-164)
+  for (int i = tid; i < I; i += kPrepThreads) {
+    uint32_t c[4] = {(uint32_t)i, (uint32_t)s, 0u, 0u};
+    philox4x32_10(c, (uint32_t)(seed & 0xffffffffull), (uint32_t)(seed >> 32));
+    const double u1 = 1.0 - ((double)(c[0] >> 5) * 67108864.0 + (double)(c[1] >> 6)) * (1.0 / 9007199254740992.0);
+    const double u2 = ((double)c[2] + 0.5) * (1.0 / 4294967296.0);
+    const double u3 = ((double)c[3] + 0.5) * (1.0 / 4294967296.0);
+    const double gauss = sqrt(-2.0 * log(u1)) * cos(2.0 * kPi * u2);
+    double* o = init + ((size_t)s * I + i) * 4;
+    o[0] = ang + ry_sigma * gauss;
+    o[1] = 0.0;
+    o[2] = 0.0;
+    o[3] = (2.0 * u3 - 1.0) * t_amp;
+  }
+}
+
+}  // namespace dib
+
+extern "C" {
+
+size_t frustum_prepare_workspace_bytes(int S, int I) {
+  (void)S; (void)I;
+  return 0;
+}
+
+// xyz_in [S][3][n_in_stride] f32 [dev], pred [S][n_in_stride] int8 [dev] (1 = predicted inside);
+// outputs: xyz_out [S][3][n_out_stride], label_out [S][n_out_stride], n_pts [S], init [S][I][4],
+// init_y_angle [S], degenerate [S] (1 = no predicted-inside point; registration_lsq.py:329-332).
+// n_out_stride must be a multiple of 16 and >= n_in.
+int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in, int n_in_stride, int S, int I,
+                              uint64_t seed, double ry_sigma, double t_amp, float* xyz_out, int8_t* label_out,
+                              int32_t* n_pts, double* init, double* init_y_angle, int32_t* degenerate,
+                              void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+  using namespace dib;
+  (void)workspace; (void)workspace_bytes;
+  DIB_REQUIRE(xyz_in && pred && xyz_out && label_out && n_pts && init && init_y_angle && degenerate, "NULL argument");
+  DIB_REQUIRE(S >= 0 && I >= 1 && n_in >= 0 && n_in <= n_in_stride, "bad sizes");
+  const int n_out_stride = (n_in + 15) & ~15;
+  if (S == 0) return DIB_OK;
+  frustum_prepare_kernel<<<S, kPrepThreads, 0, (cudaStream_t)stream>>>(xyz_in, pred, n_in, n_in_stride, n_out_stride,
+                                                                        I, seed, ry_sigma, t_amp, xyz_out, label_out,
+                                                                        n_pts, init, init_y_angle, degenerate);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,264 @@
+"""Host side of the registration path: thin Python over the C ABI (include/deepi2p_b200.h).
+
+torch is used only for device memory, streams and pinned host buffers; every computation is a
+hand-written sm_100a kernel reached through ctypes.  No CPU fallback exists: without a CUDA
+device or without the compiled library every entry point raises.
+
+Mirrors, in order of the reference's call stack:
+  register_batch      <- the per-sample body of evaluation/registration_lsq.py:329-343
+                         (get_initial_guess + solve_P_random_perturb), batched and on device
+  solve_batch         <- the 60 x solvePGivenK loop of registration_lsq.py:142-186, one launch
+  solve_p_given_k     <- FrustumRegistration.solvePGivenK (registration.cpp:9-186)
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _native
+
+DEFAULT_T_LB = (-5.0, -0.1, -10.0)      # registration_lsq.py:340
+DEFAULT_T_UB = (5.0, 0.1, 10.0)
+RY_SIGMA = 10.0 * math.pi / 180.0       # registration_lsq.py:339
+T_AMPLITUDE = 10.0                      # registration_lsq.py:337
+TERMINATION = ("gradient_tolerance", "parameter_tolerance", "function_tolerance", "max_iterations",
+               "min_trust_region_radius", "invalid_steps", "infeasible_start")
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _native.NativeError("deepi2p_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream_ptr(stream=None):
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def round_up(n, m):
+    return (n + m - 1) // m * m
+
+
+def pack_clouds(points, labels, device="cuda", n_pts=None, dtype=None):
+    """Host clouds -> device record (xyz [S,3,Ns], label int8 [S,Ns], n_pts int32 [S]).
+
+    points: array [S,3,N] (or [3,N]); labels: [S,N] ints (1 inside, 0 outside, anything else
+    ignored).  Coordinates are stored as float32 when that is lossless (the loaders produce
+    float32: data/kitti_pc_img_pose_loader.py:431), otherwise as float64.
+    """
+    pts = np.asarray(points)
+    lab = np.asarray(labels)
+    if pts.ndim == 2:
+        pts, lab = pts[None], lab[None]
+    S, three, N = pts.shape
+    if three != 3 or lab.shape != (S, N):
+        raise ValueError("points must be [S,3,N] and labels [S,N]")
+    if dtype is None:
+        if pts.dtype == np.float32:
+            dtype = np.float32
+        else:
+            p32 = pts.astype(np.float32)
+            dtype = np.float32 if np.array_equal(p32.astype(pts.dtype), pts) else np.float64
+    Ns = round_up(max(N, 1), 16)
+    xyz = np.zeros((S, 3, Ns), dtype=dtype)
+    xyz[:, :, :N] = pts
+    l8 = np.full((S, Ns), -1, dtype=np.int8)
+    l8[:, :N] = np.where(lab == 1, 1, np.where(lab == 0, 0, -1))
+    if n_pts is None:
+        n_pts = np.full(S, N, dtype=np.int32)
+    dev = torch.device(device)
+    return (torch.from_numpy(xyz).to(dev), torch.from_numpy(l8).to(dev),
+            torch.from_numpy(np.asarray(n_pts, dtype=np.int32)).to(dev))
+
+
+def _as_K(K, S, device):
+    K = torch.as_tensor(K, dtype=torch.float64)
+    if K.numel() == 9:
+        K = K.reshape(1, 9).expand(S, 9)
+    K = K.reshape(S, 9).contiguous()
+    return K.to(device)
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB, max_iter=500,
+                is_2d=True, return_all=False, stream=None):
+    """Batched multi-start solve, everything resident on the device.
+
+    xyz [S,3,Ns] f32|f64 cuda, label [S,Ns] int8 cuda, n_pts [S] int32 cuda or None,
+    K [S,9]|[9]|[3,3] f64, init [S,I,4] f64 = (init_y_angle, Tx, Ty, Tz) per problem.
+    Returns dict(P [S,4,4], cost [S], best [S]) (+ params [S,I,6], costs [S,I], stats [S,I,4]
+    = (LM iterations, cloud passes, line-search contractions, termination) if return_all).
+    """
+    _require_cuda()
+    lib = _native.load()
+    if not (xyz.is_cuda and label.is_cuda):
+        raise ValueError("xyz/label must be CUDA tensors")
+    if xyz.dtype not in (torch.float32, torch.float64) or label.dtype != torch.int8:
+        raise ValueError("xyz must be float32/float64 and label int8")
+    if not (xyz.is_contiguous() and label.is_contiguous()):
+        raise ValueError("xyz/label must be contiguous")
+    S, three, Ns = xyz.shape
+    if three != 3 or tuple(label.shape) != (S, Ns):
+        raise ValueError("shape mismatch")
+    dev = xyz.device
+    init = torch.as_tensor(init, dtype=torch.float64).to(dev).contiguous()
+    if init.dim() != 3 or init.shape[0] != S or init.shape[2] != 4:
+        raise ValueError("init must be [S,I,4]")
+    I = init.shape[1]
+    K9 = _as_K(K, S, dev)
+    if n_pts is not None:
+        n_pts = n_pts.to(dev, torch.int32).contiguous()
+    lb = np.ascontiguousarray(np.asarray(t_lb, dtype=np.float64).reshape(3))
+    ub = np.ascontiguousarray(np.asarray(t_ub, dtype=np.float64).reshape(3))
+    with torch.cuda.device(dev):
+        P = torch.empty((S, 4, 4), dtype=torch.float64, device=dev)
+        cost = torch.empty((S,), dtype=torch.float64, device=dev)
+        best = torch.empty((S,), dtype=torch.int32, device=dev)
+        params = costs = stats = None
+        if return_all:
+            params = torch.empty((S, I, 6), dtype=torch.float64, device=dev)
+            costs = torch.empty((S, I), dtype=torch.float64, device=dev)
+            stats = torch.empty((S, I, 4), dtype=torch.int32, device=dev)
+        wsb = lib.frustum_solve_workspace_bytes(S, I)
+        ws = _workspace(wsb, dev)
+        fn = lib.frustum_solve_batch_f32 if xyz.dtype == torch.float32 else lib.frustum_solve_batch_f64
+        rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(init), lb.ctypes.data, ub.ctypes.data,
+                float(H), float(W), int(max_iter), 1 if is_2d else 0, S, I, _ptr(P), _ptr(cost), _ptr(best),
+                _ptr(params), _ptr(costs), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(stream))
+    _native.check(rc, "frustum_solve_batch")
+    out = dict(P=P, cost=cost, best=best)
+    if return_all:
+        out.update(params=params, costs=costs, stats=stats)
+    return out
+
+
+def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None):
+    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook)."""
+    _require_cuda()
+    lib = _native.load()
+    S, _, Ns = xyz.shape
+    dev = xyz.device
+    K9 = _as_K(K, S, dev)
+    x = torch.as_tensor(x, dtype=torch.float64).to(dev).contiguous().reshape(S, 6)
+    with torch.cuda.device(dev):
+        cost = torch.empty((S,), dtype=torch.float64, device=dev)
+        grad = torch.empty((S, 6), dtype=torch.float64, device=dev)
+        JtJ = torch.empty((S, 36), dtype=torch.float64, device=dev)
+        fn = lib.frustum_evaluate_f32 if xyz.dtype == torch.float32 else lib.frustum_evaluate_f64
+        rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(x), float(H), float(W), 1 if is_2d else 0, S,
+                _ptr(cost), _ptr(grad), _ptr(JtJ), _stream_ptr(stream))
+    _native.check(rc, "frustum_evaluate")
+    P = 4 if is_2d else 6
+    return cost, grad[:, :P], JtJ[:, :P * P].reshape(S, P, P)
+
+
+def residuals(xyz, label, n, K, x, H, W, is_2d=True, stream=None):
+    """Loss-corrected residual vector of one cloud at x (registration.cpp:150-155)."""
+    _require_cuda()
+    lib = _native.load()
+    dev = xyz.device
+    Ns = xyz.shape[-1]
+    lab = label.reshape(-1)[:n]
+    rows = torch.where(lab == 1, 3, torch.where(lab == 0, 1, 0)).to(torch.int32)
+    offs = (torch.cumsum(rows, 0, dtype=torch.int32) - rows).contiguous()
+    total = int(rows.sum().item())
+    K9 = _as_K(K, 1, dev)
+    xx = torch.zeros(6, dtype=torch.float64, device=dev)
+    xv = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
+    xx[:xv.numel()] = xv.to(dev)
+    with torch.cuda.device(dev):
+        res = torch.zeros((max(total, 1),), dtype=torch.float64, device=dev)
+        fn = lib.frustum_residuals_f32 if xyz.dtype == torch.float32 else lib.frustum_residuals_f64
+        rc = fn(_ptr(xyz), _ptr(label), int(n), Ns, _ptr(K9), _ptr(xx), float(H), float(W), 1 if is_2d else 0,
+                _ptr(offs), _ptr(res), _stream_ptr(stream))
+    _native.check(rc, "frustum_residuals")
+    return res[:total]
+
+
+def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=T_AMPLITUDE, stream=None):
+    """On-device get_initial_guess + init perturbation (registration_lsq.py:196-220, 163-164).
+
+    xyz_in [S,3,Ns_in] f32 cuda, pred [S,Ns_in] int8 cuda.  Returns dict(xyz, label, n_pts, init,
+    init_y_angle, degenerate) ready for solve_batch."""
+    _require_cuda()
+    lib = _native.load()
+    S, _, Ns_in = xyz_in.shape
+    dev = xyz_in.device
+    if xyz_in.dtype != torch.float32 or pred.dtype != torch.int8:
+        raise ValueError("prepare_batch takes float32 coordinates and int8 predictions")
+    Ns = round_up(max(int(n_in), 1), 16)
+    with torch.cuda.device(dev):
+        xyz = torch.empty((S, 3, Ns), dtype=torch.float32, device=dev)
+        label = torch.empty((S, Ns), dtype=torch.int8, device=dev)
+        n_pts = torch.empty((S,), dtype=torch.int32, device=dev)
+        init = torch.empty((S, n_inits, 4), dtype=torch.float64, device=dev)
+        ang = torch.empty((S,), dtype=torch.float64, device=dev)
+        degen = torch.empty((S,), dtype=torch.int32, device=dev)
+        rc = lib.frustum_prepare_batch_f32(_ptr(xyz_in), _ptr(pred), int(n_in), Ns_in, S, int(n_inits), int(seed),
+                                           float(ry_sigma), float(t_amp), _ptr(xyz), _ptr(label), _ptr(n_pts),
+                                           _ptr(init), _ptr(ang), _ptr(degen), 0, 0, _stream_ptr(stream))
+    _native.check(rc, "frustum_prepare_batch")
+    return dict(xyz=xyz, label=label, n_pts=n_pts, init=init, init_y_angle=ang, degenerate=degen)
+
+
+def register_batch(xyz_in, pred, n_in, K, H, W, n_inits=60, seed=0, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB,
+                   max_iter=500, is_2d=True, return_all=False, stream=None):
+    """Batched body of registration_lsq.py:329-343: initial guess, front filter, n_inits perturbed
+    starts, min-cost pose; degenerate samples (no predicted-inside point) get P = I, cost = 1e4."""
+    prep = prepare_batch(xyz_in, pred, n_in, n_inits, seed=seed, stream=stream)
+    out = solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K, prep["init"], H, W, t_lb, t_ub, max_iter,
+                      is_2d, return_all=return_all, stream=stream)
+    deg = prep["degenerate"].bool()
+    eye = torch.eye(4, dtype=torch.float64, device=out["P"].device)
+    out["P"] = torch.where(deg[:, None, None], eye, out["P"])
+    out["cost"] = torch.where(deg, torch.full_like(out["cost"], 1e4), out["cost"])
+    out["init_y_angle"] = prep["init_y_angle"]
+    out["n_pts"] = prep["n_pts"]
+    out["degenerate"] = prep["degenerate"]
+    return out
+
+
+def solve_p_given_k(points, labels, K, init_y_angle, init_T, H, W, t_xyz_lower_bound, t_xyz_upper_bound,
+                    max_iter, is_debug, is_2d):
+    """Drop-in body of FrustumRegistration.solvePGivenK (registration.cpp:190-206): numpy in,
+    (P 4x4 ndarray, final_cost float, residuals ndarray) out."""
+    _require_cuda()
+    pts = np.asarray(points, dtype=np.float64)
+    if pts.ndim != 2 or pts.shape[0] != 3:
+        raise TypeError("points must be a 3xN float array")
+    lab = np.asarray(labels)
+    if lab.ndim != 1 or lab.shape[0] != pts.shape[1]:
+        raise TypeError("labels must be a length-N integer array")
+    lb = list(t_xyz_lower_bound)
+    ub = list(t_xyz_upper_bound)
+    if len(lb) < 3 or len(ub) < 3:
+        raise IndexError("bounds need 3 entries")       # std::out_of_range in the reference (:131-134)
+    T = np.asarray(init_T, dtype=np.float64).reshape(3)
+    xyz, l8, n_pts = pack_clouds(pts, lab)
+    init = torch.tensor([[[float(init_y_angle), T[0], T[1], T[2]]]], dtype=torch.float64)
+    out = solve_batch(xyz, l8, n_pts, np.asarray(K, dtype=np.float64), init, H, W, lb[:3], ub[:3], int(max_iter),
+                      bool(is_2d), return_all=True)
+    P = 4 if is_2d else 6
+    x = out["params"][0, 0, :P]
+    res = residuals(xyz[0], l8[0], pts.shape[1], np.asarray(K, dtype=np.float64), x, H, W, bool(is_2d))
+    if is_debug:
+        st = out["stats"][0, 0].tolist()
+        print("deepi2p_b200 solvePGivenK: iterations=%d evaluations=%d line_search_steps=%d termination=%s cost=%.6e"
+              % (st[0], st[1], st[2], TERMINATION[st[3]] if 0 <= st[3] < len(TERMINATION) else st[3],
+                 float(out["cost"][0])))
+    return out["P"][0].cpu().numpy(), float(out["cost"][0].item()), res.cpu().numpy()

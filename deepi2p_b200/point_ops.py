@@ -1,0 +1,57 @@
+"""Host side of index_max / ball_query: torch tensors in, torch tensors out, kernels via the C ABI.
+
+Mirrors the reference's extension modules (models/index_max_ext/index_max.cpp:119-159,
+models/ball_query_ext/ball_query.cpp:23-48): same argument checks (CUDA + contiguous ->
+RuntimeError), output allocated on the input's device, int32 outputs.  Unlike the reference the
+kernels are launched on torch's *current* stream of the tensor's device, not the legacy default
+stream.
+"""
+import torch
+
+from . import _native
+
+
+def _check_input(t, name, dtype):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor/variable")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must have dtype {dtype}")
+
+
+def index_max_forward(data, index, K):
+    """out[b,c,k] = lowest n with index[b,n]==k attaining max data[b,c,n] over that segment if
+    that max > -1000, else 0 (index_max_cuda.cu:30-62)."""
+    _check_input(data, "data", torch.float32)
+    _check_input(index, "index", torch.int32)
+    if data.dim() != 3 or index.dim() != 2 or index.shape[0] != data.shape[0] or index.shape[1] != data.shape[2]:
+        raise RuntimeError("data must be [B,C,N] and index [B,N]")
+    lib = _native.load()
+    B, C, N = data.shape
+    K = int(K)
+    with torch.cuda.device(data.device):
+        out = torch.empty((B, C, K), dtype=torch.int32, device=data.device)
+        rc = lib.index_max_forward(data.data_ptr(), index.data_ptr(), out.data_ptr(), B, C, N, K,
+                                   torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "index_max_forward")
+    return out
+
+
+def ball_query_forward(node_to_point_dist, radius, K):
+    """out[b,m,:] = first K indices n (ascending) with dist[b,m,n] <= radius; none -> 0; fewer ->
+    cyclic repeat (ball_query_cuda.cu:11-50)."""
+    _check_input(node_to_point_dist, "node_to_point_dist", torch.float32)
+    if node_to_point_dist.dim() != 3:
+        raise RuntimeError("node_to_point_dist must be [B,M,N]")
+    lib = _native.load()
+    B, M, N = node_to_point_dist.shape
+    K = int(K)
+    with torch.cuda.device(node_to_point_dist.device):
+        out = torch.empty((B, M, K), dtype=torch.int32, device=node_to_point_dist.device)
+        rc = lib.ball_query_forward(node_to_point_dist.data_ptr(), float(radius), out.data_ptr(), B, M, N, K,
+                                    torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "ball_query_forward")
+    return out

@@ -1,0 +1,133 @@
+/* deepi2p_b200 -- C ABI of the B200-native inverse-camera-projection registration path.
+ *
+ * Plain C, no torch / pybind types: every pointer marked [dev] is a CUDA device pointer owned
+ * by the caller, every launch goes to the cudaStream_t the caller passes (0 = legacy default
+ * stream), nothing is retained between calls, no call throws.  Return value: 0 on success or a
+ * negative DIB_E* code; dib_last_error() gives a thread-local message.
+ *
+ * Each entry point replaces one interface of the reference (lijx10/DeepI2P @ cd21389):
+ *
+ *   frustum_solve_batch_*   FrustumRegistration.solvePGivenK          evaluation/frustum_reg/src/registration.cpp:9-186,190-206
+ *                           + the multi-start loop around it          evaluation/registration_lsq.py:127-186
+ *   frustum_residuals_*     the residual vector solvePGivenK returns  registration.cpp:150-155
+ *   frustum_evaluate_*      (test hook: one cost/gradient/JtJ pass)   registration_{2d,3d}.hpp:34-68,105-127
+ *   frustum_prepare_batch   get_initial_guess + init perturbation     evaluation/registration_lsq.py:196-220,163-164
+ *   index_max_forward       index_max.forward_cuda[_shared_mem]       models/index_max_ext/index_max_cuda.cu:30-62,84-100
+ *   ball_query_forward      ball_query.forward_cuda_shared_mem        models/ball_query_ext/ball_query_cuda.cu:11-50,54-71
+ *
+ * INTEGRATION.md shows the binding a maintainer of the reference would add for each.
+ */
+#ifndef DEEPI2P_B200_H_
+#define DEEPI2P_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIB_OK 0
+#define DIB_EINVAL (-22)   /* bad argument (shape, alignment, NULL)            */
+#define DIB_ENOMEM (-12)   /* workspace too small                              */
+#define DIB_ECUDA (-5)     /* a CUDA runtime call failed; see dib_last_error() */
+#define DIB_ENODEV (-19)   /* no sm_100 device                                 */
+
+typedef void* dib_stream_t; /* cudaStream_t */
+
+/* ABI version (bumped on any signature change) and last error text of the calling thread. */
+int dib_abi_version(void);
+const char* dib_last_error(void);
+/* Number of SMs of the current device, or a negative error code. */
+int dib_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Registration solver.
+ *
+ * Device record of a cloud (13 B / point, or 25 B / point for the f64 variant):
+ *   xyz    [S][3][n_stride]  coordinates, struct-of-arrays per sample   (f32 or f64)
+ *   label  [S][n_stride]     int8: 1 = predicted inside the image, 0 = outside, else ignored
+ *   n_pts  [S]               int32 valid prefix length per sample (NULL = n_stride everywhere)
+ * n_stride must be a multiple of 16 and the base pointers 16-byte aligned (bulk-copy staging).
+ *
+ * One problem = (sample s, init i).  Parameter vector as in registration.cpp:24-50:
+ *   is_2d: x = [ry, tx, ty, tz];   else: x = [ax, ay, az, tx, ty, tz] started at [0, ry, 0, T].
+ *   init   [S][I][4]  f64  (init_y_angle, Tx, Ty, Tz) per problem
+ *   K9     [S][9]     f64  row-major intrinsics; fx=K[0], fy=K[4], cx=K[2], cy=K[5]
+ *   lb3/ub3 HOST pointers to 3 doubles: box bounds on the translation (registration.cpp:128-135)
+ * Outputs per sample (arg-min of final cost over the I inits, lowest index wins ties):
+ *   P16_out [S][16] f64 row-major 4x4 pose, cost_out [S] f64, best_out [S] int32 (may be NULL)
+ * Optional per-problem outputs (each may be NULL):
+ *   params_all [S][I][6] f64, cost_all [S][I] f64,
+ *   stats_all  [S][I][4] int32 = (LM iterations, cloud passes (evaluations), line-search
+ *                                 contractions, termination code)
+ * Termination codes: 0 gradient tol, 1 parameter tol, 2 function tol, 3 max iterations,
+ *   4 min trust-region radius, 5 too many invalid steps, 6 infeasible start (init returned).
+ * workspace: [dev] scratch of at least frustum_solve_workspace_bytes(S, I) bytes.
+ * ------------------------------------------------------------------------------------------ */
+size_t frustum_solve_workspace_bytes(int S, int I);
+
+int frustum_solve_batch_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                            const double* K9, const double* init, const double* lb3, const double* ub3,
+                            double H, double W, int max_iter, int is_2d, int S, int I,
+                            double* P16_out, double* cost_out, int32_t* best_out,
+                            double* params_all, double* cost_all, int32_t* stats_all,
+                            void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
+int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                            const double* K9, const double* init, const double* lb3, const double* ub3,
+                            double H, double W, int max_iter, int is_2d, int S, int I,
+                            double* P16_out, double* cost_out, int32_t* best_out,
+                            double* params_all, double* cost_all, int32_t* stats_all,
+                            void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
+/* One evaluation pass per sample at explicit parameters x [S][6] f64:
+ * cost_out [S], grad_out [S][6] (J^T r), JtJ_out [S][36] (row-major P x P in the top-left). */
+int frustum_evaluate_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                         const double* K9, const double* x, double H, double W, int is_2d, int S,
+                         double* cost_out, double* grad_out, double* JtJ_out, dib_stream_t stream);
+int frustum_evaluate_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                         const double* K9, const double* x, double H, double W, int is_2d, int S,
+                         double* cost_out, double* grad_out, double* JtJ_out, dib_stream_t stream);
+
+/* Loss-corrected residual vector at x (single cloud), in point order, one row per label-0 point
+ * and three per label-1 point (registration.cpp:150-155).  row_offset [n] int32 [dev] = exclusive
+ * prefix of rows per point (caller-computed); residuals [rows] f64 [dev]. */
+int frustum_residuals_f32(const float* xyz, const int8_t* label, int n, int n_stride, const double* K9,
+                          const double* x, double H, double W, int is_2d, const int32_t* row_offset,
+                          double* residuals, dib_stream_t stream);
+int frustum_residuals_f64(const double* xyz, const int8_t* label, int n, int n_stride, const double* K9,
+                          const double* x, double H, double W, int is_2d, const int32_t* row_offset,
+                          double* residuals, dib_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Front end of the multi-start driver, on device (registration_lsq.py:196-220 get_initial_guess,
+ * :163-164 perturbed inits, :329-332 degenerate-sample flag).
+ *   xyz_in [S][3][n_in_stride] f32, pred [S][n_in_stride] int8 (1 = predicted inside), n_in valid.
+ * Outputs (n_out_stride = round_up(n_in, 16)):
+ *   xyz_out [S][3][n_out_stride] f32, label_out [S][n_out_stride] int8 : front-filtered cloud in
+ *       the original point order, tail padded with ignored points; n_pts [S] int32 = points kept
+ *   init [S][I][4] f64 : (init_y_angle + N(0, ry_sigma), 0, 0, U(-t_amp, t_amp)), Philox4x32-10
+ *       counter (init, sample, 0, 0), key = seed
+ *   init_y_angle [S] f64, degenerate [S] int32 (1 = no predicted-inside point)
+ * ------------------------------------------------------------------------------------------ */
+size_t frustum_prepare_workspace_bytes(int S, int I);
+int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in, int n_in_stride, int S, int I,
+                              uint64_t seed, double ry_sigma, double t_amp, float* xyz_out, int8_t* label_out,
+                              int32_t* n_pts, double* init, double* init_y_angle, int32_t* degenerate,
+                              void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Segmented arg-max (index_max) and first-K-in-radius (ball_query).  Bit-exact index outputs.
+ *   data  [B][C][N] f32, index [B][N] int32 in [0,K), out [B][C][K] int32
+ *   dist  [B][M][N] f32, out [B][M][K] int32
+ * ------------------------------------------------------------------------------------------ */
+int index_max_forward(const float* data, const int32_t* index, int32_t* out,
+                      int B, int C, int N, int K, dib_stream_t stream);
+int ball_query_forward(const float* dist, float radius, int32_t* out,
+                       int B, int M, int N, int K, dib_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEEPI2P_B200_H_ */

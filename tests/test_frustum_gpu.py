@@ -1,0 +1,306 @@
+"""GPU parity tests of the registration solver: CUDA path (through the C ABI) vs the CPU oracle.
+
+Tolerances (BASELINE.json north_star): pose within 1e-4 rad / 1e-3 m of the oracle; single
+evaluations (cost / gradient / J^T J) agree to 1e-9 relative (fp64 both sides, different
+summation order and analytic-vs-dual-number derivatives).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from deepi2p_b200 import frustum, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+
+ROT_TOL = 1e-4
+TRANS_TOL = 1e-3
+
+
+def rot_angle(Ra, Rb):
+    c = (np.trace(Ra.T @ Rb) - 1.0) / 2.0
+    return math.acos(max(-1.0, min(1.0, c)))
+
+
+def pose_err(Pa, Pb):
+    return rot_angle(Pa[:3, :3], Pb[:3, :3]), float(np.linalg.norm(Pa[:3, 3] - Pb[:3, 3]))
+
+
+def small_sample(seed, n=2048):
+    return syn.make_sample(seed, n_points=n)
+
+
+@pytest.mark.parametrize("is_2d", [True, False])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_evaluate_matches_oracle(cuda, is_2d, dtype):
+    rng = np.random.default_rng(7)
+    S = 4
+    samples = [small_sample(100 + s, 3000 + 17 * s) for s in range(S)]
+    P = 4 if is_2d else 6
+    for s, smp in enumerate(samples):
+        pts = smp["points"].astype(np.float64)
+        if dtype == np.float64:
+            pts = pts + rng.normal(0, 1e-9, pts.shape)      # not float32-representable
+        xyz, lab, n_pts = frustum.pack_clouds(pts, smp["pred"], dtype=dtype)
+        assert xyz.dtype == (torch.float32 if dtype == np.float32 else torch.float64)
+        x = np.zeros(6)
+        if is_2d:
+            x[:4] = [smp["ry_gt"] + 0.05, smp["t_gt"][0] + 0.3, 0.02, smp["t_gt"][2] - 0.5]
+        else:
+            x[:6] = [0.02, smp["ry_gt"] + 0.05, -0.03, smp["t_gt"][0] + 0.3, 0.02, smp["t_gt"][2] - 0.5]
+        c, g, A = frustum.evaluate_batch(xyz, lab, n_pts, smp["K"], x[None], smp["H"], smp["W"], is_2d)
+        co, go, Ao = oracle.evaluate(pts, smp["pred"], smp["K"], x[:P], smp["H"], smp["W"], is_2d)
+        assert abs(c.item() - co) <= 1e-10 * max(1.0, abs(co))
+        np.testing.assert_allclose(g[0].cpu().numpy(), go, rtol=1e-9, atol=1e-9 * np.abs(go).max())
+        np.testing.assert_allclose(A[0].cpu().numpy(), Ao, rtol=1e-9, atol=1e-9 * np.abs(Ao).max())
+
+
+def test_evaluate_small_angle_branch(cuda):
+    smp = small_sample(3)
+    pts = smp["points"].astype(np.float64)
+    xyz, lab, n_pts = frustum.pack_clouds(pts, smp["pred"])
+    for is_2d, x in ((True, [1e-9, 0.1, 0.0, 0.2, 0, 0]), (False, [1e-9, -2e-9, 3e-9, 0.1, 0.0, 0.2]),
+                     (False, [1e-5, 2e-5, -1e-5, 0.1, 0.0, 0.2])):
+        P = 4 if is_2d else 6
+        x = np.asarray(x, dtype=np.float64)
+        c, g, A = frustum.evaluate_batch(xyz, lab, n_pts, smp["K"], x[None], smp["H"], smp["W"], is_2d)
+        co, go, Ao = oracle.evaluate(pts, smp["pred"], smp["K"], x[:P], smp["H"], smp["W"], is_2d)
+        assert abs(c.item() - co) <= 1e-10 * max(1.0, abs(co))
+        np.testing.assert_allclose(g[0].cpu().numpy(), go, rtol=1e-8, atol=1e-8 * np.abs(go).max())
+        np.testing.assert_allclose(A[0].cpu().numpy(), Ao, rtol=1e-8, atol=1e-8 * np.abs(Ao).max())
+
+
+@pytest.mark.parametrize("is_2d", [True, False])
+def test_solve_matches_oracle(cuda, is_2d):
+    """Trajectory-level parity: every (sample, init) solve lands on the oracle's pose."""
+    S, I, n = 6, 5, 4096
+    xs, ls, inits, Ks = [], [], [], []
+    smps = []
+    for s in range(S):
+        smp = small_sample(200 + s, n)
+        iy, _, _, _ = oracle.initial_guess(smp["points"], smp["pred"])
+        ry, t = syn.make_inits(200 + s, iy, I)
+        smps.append((smp, ry, t))
+        xs.append(smp["points"]); ls.append(smp["pred"]); Ks.append(smp["K"].reshape(9))
+        inits.append(np.concatenate([ry[:, None], t], axis=1))
+    xyz, lab, n_pts = frustum.pack_clouds(np.stack(xs), np.stack(ls))
+    out = frustum.solve_batch(xyz, lab, n_pts, np.stack(Ks), np.stack(inits), smps[0][0]["H"], smps[0][0]["W"],
+                              syn.T_LB, syn.T_UB, 500, is_2d, return_all=True)
+    params = out["params"].cpu().numpy()
+    costs = out["costs"].cpu().numpy()
+    stats = out["stats"].cpu().numpy()
+    worst_r = worst_t = 0.0
+    for s, (smp, ry, t) in enumerate(smps):
+        ms = oracle.solve_multistart(smp["points"], smp["pred"], smp["K"], ry, t, smp["H"], smp["W"], syn.T_LB,
+                                     syn.T_UB, 500, is_2d)
+        P = 4 if is_2d else 6
+        for i in range(I):
+            if is_2d:
+                dr = abs(params[s, i, 0] - ms["params"][i, 0])
+                dt = np.linalg.norm(params[s, i, 1:4] - ms["params"][i, 1:4])
+            else:
+                dr = np.linalg.norm(params[s, i, 0:3] - ms["params"][i, 0:3])
+                dt = np.linalg.norm(params[s, i, 3:6] - ms["params"][i, 3:6])
+            worst_r, worst_t = max(worst_r, dr), max(worst_t, dt)
+            assert dr < ROT_TOL and dt < TRANS_TOL, (s, i, params[s, i, :P], ms["params"][i, :P], stats[s, i],
+                                                     ms["stats"][i])
+            assert abs(costs[s, i] - ms["costs"][i]) <= 1e-6 * max(1.0, ms["costs"][i])
+            assert stats[s, i, 0] == ms["stats"][i]["iterations"]
+            assert stats[s, i, 1] == ms["stats"][i]["unique_evals"]
+            assert stats[s, i, 3] == ms["stats"][i]["termination"]
+        # arg-min over inits and the 4x4
+        assert int(out["best"][s]) == ms["best"]
+        er, et = pose_err(out["P"][s].cpu().numpy(), ms["P"])
+        assert er < ROT_TOL and et < TRANS_TOL
+        assert abs(out["cost"][s].item() - ms["cost"]) <= 1e-6 * max(1.0, ms["cost"])
+    print("worst param diff: rot %.3e rad, trans %.3e m" % (worst_r, worst_t))
+
+
+def test_known_answer_zero_cost_start(cuda):
+    """Exact GT labels + start at the GT pose => cost 0 => the init pose comes back bit for bit."""
+    smp = small_sample(5)
+    xyz, lab, n_pts = frustum.pack_clouds(smp["points"], smp["gt"])
+    init = np.array([[[smp["ry_gt"], *smp["t_gt"]]]])
+    for is_2d in (True, False):
+        out = frustum.solve_batch(xyz, lab, n_pts, smp["K"], init, smp["H"], smp["W"], [-100] * 3, [100] * 3, 500,
+                                  is_2d, return_all=True)
+        assert out["cost"].item() == 0.0
+        st = out["stats"][0, 0].tolist()
+        assert st[0] == 0 and st[1] == 1 and st[3] == 0
+        p = out["params"][0, 0].cpu().numpy()
+        if is_2d:
+            assert p[0] == smp["ry_gt"] and np.array_equal(p[1:4], smp["t_gt"])
+        else:
+            assert p[1] == smp["ry_gt"] and p[0] == 0 and p[2] == 0 and np.array_equal(p[3:6], smp["t_gt"])
+        er, et = pose_err(out["P"][0].cpu().numpy(), smp["P_gt"])
+        assert er < 1e-12 and et < 1e-12
+
+
+def test_infeasible_start_returns_init(cuda):
+    smp = small_sample(6)
+    xyz, lab, n_pts = frustum.pack_clouds(smp["points"], smp["pred"])
+    init = np.array([[[0.3, 0.0, 0.5, 1.0]]])       # ty = 0.5 outside [-0.1, 0.1]
+    out = frustum.solve_batch(xyz, lab, n_pts, smp["K"], init, smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500, True,
+                              return_all=True)
+    assert out["stats"][0, 0, 3].item() == 6
+    np.testing.assert_array_equal(out["params"][0, 0, :4].cpu().numpy(), [0.3, 0.0, 0.5, 1.0])
+    Po, co, _, st, _ = oracle.solve(smp["points"], smp["pred"], smp["K"], 0.3, [0.0, 0.5, 1.0], smp["H"], smp["W"],
+                                    syn.T_LB, syn.T_UB)
+    assert st["termination"] == 6
+    er, et = pose_err(out["P"][0].cpu().numpy(), Po)
+    assert er < 1e-12 and et < 1e-12
+
+
+def test_ragged_empty_and_ignored_labels(cuda):
+    """n_pts shorter than the stride, an empty cloud, labels outside {0,1} ignored, n not a
+    multiple of the tile or of 16."""
+    n = 3001
+    smp = small_sample(9, n)
+    pred = smp["pred"].copy()
+    pred[::7] = 5                     # ignored (registration.cpp:89,106)
+    pts = np.stack([smp["points"], smp["points"], smp["points"]])
+    labs = np.stack([pred, pred, pred])
+    n_pts = np.array([n, 1777, 0], dtype=np.int32)
+    xyz, lab, npd = frustum.pack_clouds(pts, labs, n_pts=n_pts)
+    iy, _, _, _ = oracle.initial_guess(smp["points"], smp["pred"])
+    ry, t = syn.make_inits(9, iy, 3)
+    init = np.concatenate([ry[:, None], t], axis=1)[None].repeat(3, axis=0)
+    out = frustum.solve_batch(xyz, lab, npd, smp["K"], init, smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500, True,
+                              return_all=True)
+    for s, m in enumerate(n_pts):
+        for i in range(3):
+            Po, co, _, st, xo = oracle.solve(smp["points"][:, :m], pred[:m], smp["K"], ry[i], t[i], smp["H"],
+                                             smp["W"], syn.T_LB, syn.T_UB)
+            p = out["params"][s, i].cpu().numpy()
+            assert abs(p[0] - xo[0]) < ROT_TOL and np.linalg.norm(p[1:4] - xo[1:4]) < TRANS_TOL
+            assert out["stats"][s, i, 3].item() == st["termination"]
+    # empty cloud: zero cost, init returned
+    assert out["costs"][2, 0].item() == 0.0
+
+
+def test_residual_vector_and_dropin(cuda):
+    import deepi2p_b200
+    deepi2p_b200.install_dropins()
+    import FrustumRegistration
+    smp = small_sample(11, 2500)
+    iy, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+    for is_2d in (True, False):
+        P, cost, res = FrustumRegistration.solvePGivenK(pf.astype(np.float64), lf.astype(np.int64), smp["K"], iy,
+                                                        np.array([0.0, 0.0, 1.5]), smp["H"], smp["W"],
+                                                        [-5, -0.1, -10], [5, 0.1, 10], 500, False, is_2d)
+        Po, co, ro, st, xo = oracle.solve(pf, lf, smp["K"], iy, [0.0, 0.0, 1.5], smp["H"], smp["W"], syn.T_LB,
+                                          syn.T_UB, 500, is_2d)
+        assert isinstance(P, np.ndarray) and P.shape == (4, 4) and isinstance(cost, float)
+        assert res.shape == ro.shape
+        er, et = pose_err(P, Po)
+        assert er < ROT_TOL and et < TRANS_TOL
+        assert abs(cost - co) <= 1e-6 * max(1.0, co)
+        np.testing.assert_allclose(res, ro, rtol=0, atol=1e-5)
+    assert FrustumRegistration.solve is FrustumRegistration.solvePGivenK
+
+
+def philox4x32_10(c, k0, k1):
+    c = [np.asarray(v, dtype=np.uint64) for v in c]
+    k0 = np.uint64(k0); k1 = np.uint64(k1)
+    M0, M1, MASK = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0 = M0 * c[0]; p1 = M1 * c[2]
+        hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+        hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+        c = [hi1 ^ c[1] ^ k0, lo1, hi0 ^ c[3] ^ k1, lo0]
+        k0 = (k0 + np.uint64(0x9E3779B9)) & MASK
+        k1 = (k1 + np.uint64(0xBB67AE85)) & MASK
+    return c
+
+
+def test_prepare_matches_initial_guess(cuda):
+    """On-device get_initial_guess / front filter / inits vs the CPU restatement."""
+    S, n, I, seed = 5, 3333, 60, 1234
+    smps = [small_sample(300 + s, n) for s in range(S)]
+    # make the front filter bite: clean predictions for sample 0, no inside prediction for sample 4
+    smps[0]["pred"] = smps[0]["gt"].copy()
+    smps[4]["pred"] = np.zeros(n, dtype=np.int32)
+    xyz_in, pred_in, _ = frustum.pack_clouds(np.stack([s["points"] for s in smps]),
+                                             np.stack([s["pred"] for s in smps]))
+    prep = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=seed)
+    npts = prep["n_pts"].cpu().numpy()
+    for s, smp in enumerate(smps):
+        if s == 4:
+            assert prep["degenerate"][s].item() == 1 and npts[s] == n
+            continue
+        iy, pf, lf, mask = oracle.initial_guess(smp["points"], smp["pred"])
+        assert prep["degenerate"][s].item() == 0
+        assert abs(prep["init_y_angle"][s].item() - iy) < 1e-12
+        assert npts[s] == mask.sum()
+        np.testing.assert_array_equal(prep["xyz"][s, :, :npts[s]].cpu().numpy(), pf.astype(np.float32))
+        np.testing.assert_array_equal(prep["label"][s, :npts[s]].cpu().numpy(), lf.astype(np.int8))
+        assert (prep["label"][s, npts[s]:] == -1).all()
+        c = philox4x32_10([np.arange(I), np.full(I, s), np.zeros(I), np.zeros(I)], seed & 0xFFFFFFFF, seed >> 32)
+        u1 = 1.0 - ((c[0] >> np.uint64(5)).astype(np.float64) * 67108864.0
+                    + (c[1] >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
+        u2 = (c[2].astype(np.float64) + 0.5) / 4294967296.0
+        u3 = (c[3].astype(np.float64) + 0.5) / 4294967296.0
+        ry = iy + frustum.RY_SIGMA * np.sqrt(-2.0 * np.log(u1)) * np.cos(2.0 * np.pi * u2)
+        tz = (2.0 * u3 - 1.0) * frustum.T_AMPLITUDE
+        got = prep["init"][s].cpu().numpy()
+        np.testing.assert_allclose(got[:, 0], ry, rtol=0, atol=1e-12)
+        np.testing.assert_allclose(got[:, 3], tz, rtol=0, atol=1e-12)
+        assert (got[:, 1:3] == 0).all()
+    assert npts[0] < n      # the filter removed something
+    # distribution sanity of the inits
+    allr = (prep["init"][:4, :, 0] - prep["init_y_angle"][:4, None]).cpu().numpy().ravel()
+    assert abs(allr.std() - frustum.RY_SIGMA) < 0.25 * frustum.RY_SIGMA
+    # full batched registration == oracle multistart on the prepared inputs
+    out = frustum.register_batch(xyz_in, pred_in, n, smps[0]["K"], smps[0]["H"], smps[0]["W"], n_inits=4, seed=seed)
+    prep4 = frustum.prepare_batch(xyz_in, pred_in, n, 4, seed=seed)
+    for s in (0, 1):
+        smp = smps[s]
+        _, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+        ini = prep4["init"][s].cpu().numpy()
+        ms = oracle.solve_multistart(pf, lf, smp["K"], ini[:, 0], ini[:, 1:4], smp["H"], smp["W"], syn.T_LB, syn.T_UB)
+        er, et = pose_err(out["P"][s].cpu().numpy(), ms["P"])
+        assert er < ROT_TOL and et < TRANS_TOL
+    assert out["cost"][4].item() == 1e4
+    np.testing.assert_array_equal(out["P"][4].cpu().numpy(), np.eye(4))
+
+
+def test_full_size_properties(cuda):
+    """BASELINE-size cloud (20480 points): size-independent properties instead of the oracle --
+    the returned cost equals a fresh evaluation at the returned pose, the cost never exceeds the
+    start cost, translations respect the box, and a solve restarted from its own solution stops
+    immediately at the same pose (idempotence)."""
+    S, I = 4, 6
+    smps = [syn.make_sample(400 + s) for s in range(S)]
+    xyz, lab, n_pts = frustum.pack_clouds(np.stack([s["points"] for s in smps]), np.stack([s["pred"] for s in smps]))
+    inits = []
+    for s, smp in enumerate(smps):
+        iy, _, _, _ = oracle.initial_guess(smp["points"], smp["pred"])
+        ry, t = syn.make_inits(400 + s, iy, I)
+        inits.append(np.concatenate([ry[:, None], t], axis=1))
+    inits = np.stack(inits)
+    K = smps[0]["K"]; H = smps[0]["H"]; W = smps[0]["W"]
+    out = frustum.solve_batch(xyz, lab, n_pts, K, inits, H, W, syn.T_LB, syn.T_UB, 500, True, return_all=True)
+    params = out["params"].cpu().numpy()
+    for i in range(I):
+        x = np.zeros((S, 6)); x[:, :4] = params[:, i, :4]
+        c, _, _ = frustum.evaluate_batch(xyz, lab, n_pts, K, x, H, W, True)
+        np.testing.assert_allclose(c.cpu().numpy(), out["costs"][:, i].cpu().numpy(), rtol=1e-12)
+        x0 = np.zeros((S, 6)); x0[:, :4] = inits[:, i]
+        c0, _, _ = frustum.evaluate_batch(xyz, lab, n_pts, K, x0, H, W, True)
+        assert (out["costs"][:, i] <= c0 * (1 + 1e-12)).all()
+    assert (params[:, :, 1:4] >= np.array(syn.T_LB) - 1e-15).all() and (params[:, :, 1:4] <= np.array(syn.T_UB) + 1e-15).all()
+    # best-of-I equals the min of the per-init costs, lowest index on ties
+    costs = out["costs"].cpu().numpy()
+    np.testing.assert_array_equal(out["best"].cpu().numpy(), np.argmin(costs, axis=1))
+    # restart from the solution
+    re_init = params[:, :, :4].copy()
+    out2 = frustum.solve_batch(xyz, lab, n_pts, K, re_init, H, W, syn.T_LB, syn.T_UB, 500, True, return_all=True)
+    p2 = out2["params"].cpu().numpy()
+    assert np.abs(p2[:, :, 0] - params[:, :, 0]).max() < ROT_TOL
+    assert np.abs(p2[:, :, 1:4] - params[:, :, 1:4]).max() < TRANS_TOL
+    assert (out2["stats"][:, :, 0].cpu().numpy() <= 3).all()
+    # one oracle cross-check at full size
+    ms = oracle.solve(smps[0]["points"], smps[0]["pred"], K, inits[0, 0, 0], inits[0, 0, 1:4], H, W, syn.T_LB, syn.T_UB)
+    assert abs(params[0, 0, 0] - ms[4][0]) < ROT_TOL and np.linalg.norm(params[0, 0, 1:4] - ms[4][1:4]) < TRANS_TOL

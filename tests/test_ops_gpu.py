@@ -1,0 +1,142 @@
+"""GPU parity of index_max / ball_query: bit-exact int32 outputs vs the CPU oracles, the golden
+fixtures produced by the reference's own forward_cpu, and (when oracle/_ref was built in the
+build container and travelled here) the reference's own CUDA kernels."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from deepi2p_b200 import point_ops, synthetic as syn
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def run_index_max(data, index, K):
+    d = torch.from_numpy(np.ascontiguousarray(data)).cuda()
+    i = torch.from_numpy(np.ascontiguousarray(index)).cuda()
+    return point_ops.index_max_forward(d, i, K).cpu().numpy()
+
+
+def run_ball_query(dist, radius, K):
+    d = torch.from_numpy(np.ascontiguousarray(dist)).cuda()
+    return point_ops.ball_query_forward(d, radius, K).cpu().numpy()
+
+
+@pytest.mark.parametrize("B,C,N,K", [(2, 5, 1000, 16), (3, 32, 20480, 128), (1, 1, 7, 3), (2, 7, 1023, 64),
+                                     (1, 3, 4096, 4000), (1, 2, 513, 20000)])
+def test_index_max_random(cuda, B, C, N, K):
+    data, index = syn.make_index_max_inputs(B * 1000 + C, B, C, N, K)
+    np.testing.assert_array_equal(run_index_max(data, index, K), oracle.index_max(data, index, K))
+
+
+def test_index_max_adversarial(cuda):
+    B, C, N, K = 2, 6, 2048, 32
+    rng = np.random.default_rng(0)
+    data, index = syn.make_index_max_inputs(5, B, C, N, K)
+    index[:, :] = rng.integers(0, K - 4, (B, N))          # segments K-4..K-1 empty -> 0
+    data[0, 0, :] = 1.5                                    # all ties -> lowest n per segment
+    data[0, 1, :] = -2000.0                                # everything <= -1000 -> 0
+    data[0, 2, :] = -1000.0                                # exactly the floor never wins (strict >)
+    data[0, 3, ::3] = np.nan                               # NaN never wins
+    data[0, 4, :] = np.nan                                 # all NaN -> 0
+    data[0, 5, :] = np.where(rng.uniform(size=N) < 0.5, 0.0, -0.0)   # -0 == +0: first occurrence
+    data[1, 0, :] = np.inf
+    data[1, 1, :] = rng.integers(0, 3, N).astype(np.float32)         # many ties
+    data[1, 2, 5] = 3e38
+    got = run_index_max(data, index, K)
+    np.testing.assert_array_equal(got, oracle.index_max(data, index, K))
+    assert (got[:, :, K - 4:] == 0).all()
+
+
+def test_index_max_config3_shape_property(cuda):
+    """BASELINE config 3 shape (B=64, C=64, N=16384, K=64): the oracle on a slice, and for the
+    whole output the defining property (value at the returned index is the segment max)."""
+    B, C, N, K = 64, 64, 16384, 64
+    g = torch.Generator(device="cuda").manual_seed(3)
+    data = torch.randn((B, C, N), device="cuda", generator=g)
+    index = torch.randint(0, K, (B, N), device="cuda", generator=g, dtype=torch.int32)
+    out = point_ops.index_max_forward(data, index, K)
+    sl = slice(0, 2)
+    np.testing.assert_array_equal(out[sl].cpu().numpy(),
+                                  oracle.index_max(data[sl].cpu().numpy(), index[sl].cpu().numpy(), K))
+    seg_max = torch.full((B, C, K), -float("inf"), device="cuda")
+    seg_max.scatter_reduce_(2, index.long()[:, None, :].expand(B, C, N), data, reduce="amax")
+    picked = torch.gather(data, 2, out.long())
+    assert torch.equal(picked, seg_max)
+    assert torch.equal(torch.gather(index.long()[:, None, :].expand(B, C, N), 2, out.long()),
+                       torch.arange(K, device="cuda")[None, None, :].expand(B, C, K))
+
+
+@pytest.mark.parametrize("B,M,N,K", [(2, 8, 1000, 16), (4, 64, 16384, 64), (1, 1, 5, 8), (2, 3, 33, 1), (1, 5, 700, 900)])
+def test_ball_query_random(cuda, B, M, N, K):
+    dist, radius = syn.make_ball_query_inputs(B + M, B, M, N, min(K, N))
+    np.testing.assert_array_equal(run_ball_query(dist, radius, K), oracle.ball_query(dist, radius, K))
+
+
+def test_ball_query_adversarial(cuda):
+    B, M, N, K = 1, 8, 3000, 64
+    dist, radius = syn.make_ball_query_inputs(1, B, M, N, K)
+    dist[0, 0, :] = radius + 1.0                  # cnt == 0 -> zeros
+    dist[0, 1, :] = radius + 1.0; dist[0, 1, 2999] = radius        # single hit at the end, inclusive <=
+    dist[0, 2, :] = 0.0                           # everything hits: first K
+    dist[0, 3, :] = np.nan                        # NaN never hits
+    dist[0, 4, :] = radius + 1.0; dist[0, 4, [5, 17, 2000]] = 0.0  # cnt = 3 < K -> cyclic repeat
+    dist[0, 5, :] = radius + 1.0; dist[0, 5, :63] = 0.0            # cnt = K - 1
+    got = run_ball_query(dist, radius, K)
+    np.testing.assert_array_equal(got, oracle.ball_query(dist, radius, K))
+    assert (got[0, 0] == 0).all() and (got[0, 1] == 2999).all() and (got[0, 3] == 0).all()
+    np.testing.assert_array_equal(got[0, 4, :6], [5, 17, 2000, 5, 17, 2000])
+
+
+def test_golden_index_max(cuda):
+    """Fixtures written by tests/golden/make_golden.py from the REFERENCE's own forward_cpu."""
+    files = sorted(glob.glob(os.path.join(GOLDEN, "index_max_*.npz")))
+    assert files, "golden fixtures missing"
+    for f in files:
+        z = np.load(f)
+        np.testing.assert_array_equal(run_index_max(z["data"], z["index"], int(z["K"])), z["out"])
+
+
+def _load_ref(name):
+    import importlib.util
+    ref_dir = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref")
+    cands = glob.glob(os.path.join(ref_dir, name + "*.so"))
+    if not cands:
+        pytest.skip("oracle/_ref/%s not built (needs /root/reference at build time)" % name)
+    spec = importlib.util.spec_from_file_location(name, cands[0])
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_against_reference_kernels(cuda):
+    """The reference's own CUDA kernels (compiled unmodified from /root/reference into oracle/_ref)
+    as the bit-exact checker on the GPU box."""
+    ref_im = _load_ref("index_max")
+    ref_bq = _load_ref("ball_query")
+    data, index = syn.make_index_max_inputs(77, 8, 32, 20480, 128)      # shipped model shape, B <= 1024, B*K*4 <= 48 KB
+    d, i = torch.from_numpy(data).cuda(), torch.from_numpy(index).cuda()
+    torch.cuda.synchronize()
+    want = ref_im.forward_cuda_shared_mem(d, i, 128)
+    torch.cuda.synchronize()
+    assert torch.equal(point_ops.index_max_forward(d, i, 128), want)
+    dist, radius = syn.make_ball_query_inputs(78, 8, 64, 16384, 64)
+    dd = torch.from_numpy(dist).cuda()
+    torch.cuda.synchronize()
+    want = ref_bq.forward_cuda_shared_mem(dd, radius, 64)
+    torch.cuda.synchronize()
+    assert torch.equal(point_ops.ball_query_forward(dd, radius, 64), want)
+
+
+def test_argument_checks(cuda):
+    with pytest.raises(RuntimeError):
+        point_ops.index_max_forward(torch.zeros(1, 1, 4), torch.zeros(1, 4, dtype=torch.int32), 2)   # CPU tensor
+    d = torch.zeros(2, 2, 8, device="cuda")
+    with pytest.raises(RuntimeError):
+        point_ops.index_max_forward(d.transpose(1, 2), torch.zeros(2, 2, dtype=torch.int32, device="cuda"), 2)
+    with pytest.raises(RuntimeError):
+        point_ops.ball_query_forward(torch.zeros(1, 1, 4), 1.0, 2)
