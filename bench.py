@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""Benchmark of the registration hot path (BASELINE.json metric: registrations/sec on 20480-point
+KITTI-shaped batches; SURVEY.md 8d defines the inputs and the byte accounting).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3                     # our arm (CUDA)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...                              # CPU arm (oracle port of the Ceres path)
+
+A "step" is one pass of the hot path over one batch: S_local clouds x 20480 points -> on-device
+initial guess + front filter + 60 perturbed inits -> batched LM solves -> arg-min pose per cloud
+(+ the pose all-gather when N > 1).  Weak scaling: S_local = 512 clouds per GPU, so N = 8 is
+BASELINE config 4 (4096 x 20480 x 60) exactly.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BYTES_PER_POINT = 13          # x,y,z float32 + int8 label
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="multistart60", choices=["multistart60", "single_init"])
+    ap.add_argument("--samples-per-gpu", type=int, default=None)
+    ap.add_argument("--points", type=int, default=20480)
+    ap.add_argument("--inits", type=int, default=None)
+    ap.add_argument("--is-3d", action="store_true")
+    ap.add_argument("--cpu-samples", type=int, default=3, help="registrations timed on the host cores")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ops", action="store_true", help="also time index_max / ball_query (config 3)")
+    return ap.parse_args()
+
+
+def workload_shape(args):
+    if args.workload == "multistart60":
+        return (args.samples_per_gpu or 512), (args.inits or 60)
+    return (args.samples_per_gpu or 4096), (args.inits or 1)
+
+
+def load_measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:  # noqa: BLE001
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_host_batch(first_id, S, n_points):
+    """Seeded KITTI-shaped clouds (seed = global sample id) in the layout the plugin takes:
+    xyz float32 [S,3,Ns], pred int8 [S,Ns]."""
+    from deepi2p_b200 import synthetic as syn
+    Ns = (n_points + 15) // 16 * 16
+    xyz = np.zeros((S, 3, Ns), dtype=np.float32)
+    pred = np.full((S, Ns), -1, dtype=np.int8)
+    meta = None
+    for s in range(S):
+        smp = syn.make_sample(first_id + s, n_points)
+        xyz[s, :, :n_points] = smp["points"]
+        pred[s, :n_points] = smp["pred"]
+        meta = smp
+    return xyz, pred, meta
+
+
+def cpu_registration(smp_id, n_points, n_inits, is_2d, threads):
+    """One registration on the host with the oracle port of the Ceres path (all inits, `threads` at a time)."""
+    import oracle
+    from deepi2p_b200 import synthetic as syn
+    smp = syn.make_sample(smp_id, n_points)
+    iy, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+    ry, t = syn.make_inits(smp_id, iy, n_inits)
+    ms = oracle.solve_multistart(pf, lf, smp["K"], ry, t, smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500, is_2d,
+                                 threads=threads)
+    return smp, pf, lf, ry, t, ms
+
+
+def run_reference(args):
+    """CPU arm: the oracle restatement of solvePGivenK + the 60-init driver on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle  # noqa: F401  (builds the C++ oracle if needed)
+    S_local, n_inits = workload_shape(args)
+    cores = os.cpu_count() or 1
+    is_2d = not args.is_3d
+    for w in range(args.warmup):
+        cpu_registration(10_000 + w, args.points, min(n_inits, cores), is_2d, cores)
+    t0 = time.perf_counter()
+    evals = 0
+    for k in range(args.steps):
+        out = cpu_registration(20_000 + k, args.points, n_inits, is_2d, cores)
+        evals += sum(st["unique_evals"] for st in out[5]["stats"])
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    line = {
+        "impl": "reference", "metric": "registrations/sec", "value": value, "unit": "registrations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "%s: %d-pt KITTI-shaped clouds x %d inits, max_iter 500, %s" % (
+            args.workload, args.points, n_inits, "4-DoF" if is_2d else "6-DoF"),
+            "note": "each step = ONE registration (bounded sample of the GPU arm's batch)"},
+        "cpu_baseline": {"value": value, "unit": "registrations/s", "cores": cores, "kind": "port",
+                         "sample": "%d registrations x %d inits, oracle port of the Ceres path (Ceres itself is "
+                                   "not installable offline), %d threads" % (args.steps, n_inits, cores)},
+        "e2e": {"value": value, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "mean_cloud_passes_per_solve": evals / float(args.steps * n_inits),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from deepi2p_b200 import frustum, sharding, synthetic as syn, _native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torch.distributed.run --nproc-per-node %d for --gpus %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=dev)
+    _native.load()
+
+    S_local, n_inits = workload_shape(args)
+    is_2d = not args.is_3d
+    n_points = args.points
+    xyz_h, pred_h, meta = make_host_batch(rank * S_local, S_local, n_points)
+    Kmat, H, W = meta["K"], meta["H"], meta["W"]
+    xyz_pin = torch.from_numpy(xyz_h).pin_memory()
+    pred_pin = torch.from_numpy(pred_h).pin_memory()
+    xyz_d = xyz_pin.to(dev)
+    pred_d = pred_pin.to(dev)
+    K_d = torch.as_tensor(Kmat, dtype=torch.float64).reshape(1, 9).expand(S_local, 9).contiguous().to(dev)
+    out_pin = torch.empty((S_local * world, 17), dtype=torch.float64).pin_memory()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def flush_l2():
+        flush_buf.fill_(1)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    seed_box = [0]
+
+    def step_resident():
+        seed_box[0] += 1
+        out = frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=seed_box[0],
+                                     max_iter=500, is_2d=is_2d)
+        P, c = sharding.gather_poses(out["P"], out["cost"])
+        return P, c
+
+    def step_e2e():
+        seed_box[0] += 1
+        x = xyz_pin.to(dev, non_blocking=True)
+        p = pred_pin.to(dev, non_blocking=True)
+        out = frustum.register_batch(x, p, n_points, K_d, H, W, n_inits=n_inits, seed=seed_box[0], max_iter=500,
+                                     is_2d=is_2d)
+        P, c = sharding.gather_poses(out["P"], out["cost"])
+        rec = sharding.pack_records(P, c)
+        out_pin[:rec.shape[0]].copy_(rec, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return rec.shape[0]
+
+    def timed(fn, steps):
+        total_ms = 0.0
+        for _ in range(steps):
+            flush_l2()
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- warm-up (>= 3), then the timed region with clocks sampled during it
+    for _ in range(max(args.warmup, 0)):
+        step_resident()
+    barrier()
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    smi_index = vis.split(",")[local_rank].strip() if vis else str(local_rank)
+    sampler = ClockSampler(smi_index)
+    if rank == 0:
+        sampler.start()
+    ms_total = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = S_local * world / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    e2e_value = S_local * world / (ms_e2e * 1e-3)
+    h2d = xyz_pin.numel() * 4 + pred_pin.numel()
+    d2h = S_local * world * 17 * 8
+
+    # ---- roofline of the dominant kernel: the solve launch alone, CUDA events on its stream
+    prep = frustum.prepare_batch(xyz_d, pred_d, n_points, n_inits, seed=12345)
+    frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500, is_2d=is_2d)
+    k_ms = 0.0
+    reps = max(1, min(args.steps, 3))
+    for _ in range(reps):
+        flush_l2()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500,
+                                  is_2d=is_2d, return_all=True)
+        e1.record(); e1.synchronize()
+        k_ms += e0.elapsed_time(e1)
+    k_ms /= reps
+    stats = res["stats"].to(torch.float64)
+    passes = stats[:, :, 1]
+    pts_evals = float((passes * prep["n_pts"].to(torch.float64)[:, None]).sum().item())
+    alg_bytes = BYTES_PER_POINT * pts_evals
+    peak, peak_src = load_measured_peaks()
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    compulsory = float(prep["n_pts"].sum().item()) * BYTES_PER_POINT + S_local * (72 + 8 * 4 * n_inits + 136)
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": "registrations/sec", "value": value, "unit": "registrations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {
+            "workload": "%s: %d KITTI-shaped clouds/GPU x %d pts x %d inits (%s, max_iter 500); N=8 is BASELINE "
+                        "config 4" % (args.workload, S_local, n_points, n_inits, "4-DoF" if is_2d else "6-DoF"),
+            "samples_per_gpu": S_local, "points": n_points, "inits": n_inits, "parallelism": "dp%d" % world,
+            "l2": "L2 flushed (256 MiB write) before every timed step; per-step CUDA events summed",
+            "step": "prepare (initial guess + front filter + Philox inits) + LM solve + arg-min"
+                    + (" + NCCL all-gather of [S,17] f64" if world > 1 else ""),
+        },
+        "e2e": {"value": e2e_value, "unit": "registrations/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h,
+                "note": "pinned host xyz f32 + pred int8 -> device, register_batch, poses+cost -> pinned host"},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clocks,
+        "roofline": {
+            "bound": "hbm", "kernel": "frustum_solve_kernel<float,%d>" % (4 if is_2d else 6),
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms,
+            "point_evals_per_s": pts_evals / (k_ms * 1e-3),
+            "mean_cloud_passes_per_solve": float(passes.mean().item()),
+            "mean_lm_iterations_per_solve": float(stats[:, :, 0].mean().item()),
+            "compulsory_bytes_per_launch": compulsory,
+            "traffic": None,
+            "note": "algorithmic = 13 B x points x cloud passes the solver performed (streamed model, SURVEY 8d); the "
+                    "cloud is re-read from L2/shared memory, so DRAM traffic (profiles/) is far below it",
+        },
+    }
+
+    # ---- CPU baseline + pose parity on a bounded sample (oracle port, all host cores)
+    if not args.no_cpu_baseline and world == 1 and args.cpu_samples > 0:
+        import oracle  # noqa: F401
+        cores = os.cpu_count() or 1
+        t0 = time.perf_counter()
+        cpu = [cpu_registration(rank * S_local + s, n_points, n_inits, is_2d, cores) for s in range(args.cpu_samples)]
+        dt = time.perf_counter() - t0
+        worst_r = worst_t = 0.0
+        for smp, pf, lf, ry, t, ms in cpu:
+            xyz1, lab1, np1 = frustum.pack_clouds(pf, lf)
+            init = np.concatenate([ry[:, None], t], axis=1)[None]
+            g = frustum.solve_batch(xyz1, lab1, np1, smp["K"], init, H, W, max_iter=500, is_2d=is_2d)
+            Pg = g["P"][0].cpu().numpy()
+            c = (np.trace(Pg[:3, :3].T @ ms["P"][:3, :3]) - 1.0) / 2.0
+            worst_r = max(worst_r, math.acos(max(-1.0, min(1.0, c))))
+            worst_t = max(worst_t, float(np.linalg.norm(Pg[:3, 3] - ms["P"][:3, 3])))
+        line["cpu_baseline"] = {
+            "value": args.cpu_samples / dt, "unit": "registrations/s", "cores": cores, "kind": "port",
+            "sample": "%d registrations x %d inits of the same workload, oracle port of the Ceres path, %d threads"
+                      % (args.cpu_samples, n_inits, cores)}
+        line["parity"] = {"max_rot_err_rad": worst_r, "max_trans_err_m": worst_t, "samples": args.cpu_samples,
+                          "gate": "1e-4 rad / 1e-3 m vs the CPU oracle (Ceres unavailable offline)"}
+
+    if args.ops:
+        line["ops"] = bench_ops(torch, dev, peak)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def bench_ops(torch, dev, peak):
+    """BASELINE config 3: index_max + ball_query forward, B=64, C=M=64, N=16384, K=64."""
+    from deepi2p_b200 import point_ops
+    B, C, N, K = 64, 64, 16384, 64
+    g = torch.Generator(device=dev).manual_seed(0)
+    data = torch.randn((B, C, N), device=dev, generator=g)
+    index = torch.randint(0, K, (B, N), device=dev, generator=g, dtype=torch.int32)
+    pts = torch.rand((B, N, 3), device=dev, generator=g) * 20
+    nodes = torch.rand((B, C, 3), device=dev, generator=g) * 20
+    dist_m = torch.cdist(nodes, pts).contiguous()
+    radius = float(torch.kthvalue(dist_m, K, dim=2).values.median().item())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def t(fn, reps=10):
+        for _ in range(3):
+            fn()
+        ms = 0.0
+        for _ in range(reps):
+            flush.fill_(0)
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms / reps
+
+    im_ms = t(lambda: point_ops.index_max_forward(data, index, K))
+    bq_ms = t(lambda: point_ops.ball_query_forward(dist_m, radius, K))
+    im_bytes = 4 * B * C * N + 4 * B * N + 4 * B * C * K
+    out = point_ops.ball_query_forward(dist_m, radius, K)
+    # algorithmic bytes of ball_query: up to each row's K-th hit
+    hits = (dist_m <= radius)
+    csum = hits.cumsum(2)
+    kth = torch.where(csum[:, :, -1] >= K, (csum >= K).float().argmax(2) + 1, torch.full_like(csum[:, :, -1], N))
+    bq_bytes = float(kth.sum().item()) * 4 + 4 * B * C * K
+    res = {
+        "index_max": {"us": im_ms * 1e3, "GBps": im_bytes / (im_ms * 1e-3) / 1e9, "frac": im_bytes / (im_ms * 1e-3) / 1e9 / peak,
+                      "bytes": im_bytes},
+        "ball_query": {"us": bq_ms * 1e3, "GBps_algorithmic": bq_bytes / (bq_ms * 1e-3) / 1e9,
+                       "frac_algorithmic": bq_bytes / (bq_ms * 1e-3) / 1e9 / peak, "bytes_algorithmic": bq_bytes,
+                       "bytes_upper_bound": 4 * B * C * N + 4 * B * C * K, "radius": radius},
+        "shape": {"B": B, "C": C, "M": C, "N": N, "K": K},
+    }
+    del out
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import build_ref
+        if build_ref.built("index_max") and build_ref.built("ball_query"):
+            ref_im = build_ref.load("index_max")
+            ref_bq = build_ref.load("ball_query")
+            res["index_max"]["reference_kernel_us"] = 1e3 * t(lambda: ref_im.forward_cuda_shared_mem(data, index, K), 3)
+            res["ball_query"]["reference_kernel_us"] = 1e3 * t(lambda: ref_bq.forward_cuda_shared_mem(dist_m, radius, K), 3)
+    except Exception as e:  # noqa: BLE001
+        res["reference_kernels"] = "unavailable: %s" % e
+    return res
+
+
+if __name__ == "__main__":
+    main()
