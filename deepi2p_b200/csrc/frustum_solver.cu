@@ -62,7 +62,7 @@ __host__ __device__ constexpr int tri(int P, int j, int k) {   // j <= k
 // Pose constants.
 // ------------------------------------------------------------------------------------------
 template <int P>
-__device__ void make_pose(const double* x, PoseConst* pc) {
+__device__ __noinline__ void make_pose(const double* x, PoseConst* pc) {
   if (P == 4) {
     const double ry = x[0];
     pc->t[0] = x[1]; pc->t[1] = x[2]; pc->t[2] = x[3];
@@ -235,6 +235,73 @@ __device__ __forceinline__ void point_accumulate(double px, double py, double pz
 }
 
 // ------------------------------------------------------------------------------------------
+// Conservative fp32 activity test.  Most points contribute exactly zero to cost, gradient and
+// J^T J at a given pose (an "outside" point that projects outside, an "inside" point that
+// projects inside).  Each test  u > 0, u < W1, v > 0, v < H1, Z > 0  is, for Z > 0, the sign of
+// a linear form in (x, y, z, 1) whose coefficients depend only on the pose and intrinsics:
+//     u > 0   <=>  fx X + cx Z        > 0        u < W1  <=>  fx X + (cx - W1) Z < 0
+//     v > 0   <=>  fy Y + cy Z        > 0        v < H1  <=>  fy Y + (cy - H1) Z < 0
+// The forms are evaluated in fp32 with a per-point error margin m >= 1.6 x the worst-case fp32
+// evaluation error (coefficients rounded from fp64, two/three FMAs, inputs possibly rounded from
+// fp64).  A point is skipped only if its state is decided by more than m; everything else is
+// re-evaluated exactly in fp64, so the sums are those of an all-fp64 evaluation.
+// ------------------------------------------------------------------------------------------
+struct ClassConst {
+  float zc[4], al[4], ah[4], bl[4], bh[4];
+  float G, G0;
+  int enabled;
+};
+
+__device__ __noinline__ void make_class(const PoseConst& pc, const Cam& cam, ClassConst* cc) {
+  const double gamma = 8.0 / 16777216.0;    // 8 * 2^-24
+  // the five forms kx X + ky Y + kz Z:  Z;  fx X + cx Z;  fx X + (cx - W1) Z;  fy Y + cy Z;  fy Y + (cy - H1) Z
+  const double kx[5] = {0.0, cam.fx, cam.fx, 0.0, 0.0};
+  const double ky[5] = {0.0, 0.0, 0.0, cam.fy, cam.fy};
+  const double kz[5] = {1.0, cam.cx, cam.cx - cam.W1, cam.cy, cam.cy - cam.H1};
+  float* out = cc->zc;                       // zc, al, ah, bl, bh are contiguous float[4]
+  double amax = 0.0, cmax = 0.0;
+  bool finite = true;
+#pragma unroll 1
+  for (int f = 0; f < 5; ++f) {
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+      const double c = (j < 3) ? kx[f] * pc.R[j] + ky[f] * pc.R[3 + j] + kz[f] * pc.R[6 + j]
+                               : kx[f] * pc.t[0] + ky[f] * pc.t[1] + kz[f] * pc.t[2];
+      if (j < 3) amax = fmax(amax, fabs(c)); else cmax = fmax(cmax, fabs(c));
+      const float cf = (float)c;
+      if (!isfinite(cf)) finite = false;
+      out[4 * f + j] = cf;
+    }
+  }
+  cc->G = (float)(gamma * amax * 1.0000002);
+  cc->G0 = (float)(gamma * cmax * 1.0000002) + 1e-30f;
+  cc->enabled = (finite && isfinite(cc->G) && isfinite(cc->G0)) ? 1 : 0;
+}
+
+template <int P>
+__device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab, const ClassConst& cc) {
+  if ((unsigned)lab > 1u) return false;                // labels other than 0/1 carry no residual block
+  if (!cc.enabled) return true;
+  const float m = fmaf(cc.G, fabsf(x) + fabsf(y) + fabsf(z), cc.G0);
+  float Z, al, ah;
+  if (P == 4) {                                        // R = Ry: no y terms in X and Z
+    Z = fmaf(cc.zc[0], x, fmaf(cc.zc[2], z, cc.zc[3]));
+    al = fmaf(cc.al[0], x, fmaf(cc.al[2], z, cc.al[3]));
+    ah = fmaf(cc.ah[0], x, fmaf(cc.ah[2], z, cc.ah[3]));
+  } else {
+    Z = fmaf(cc.zc[0], x, fmaf(cc.zc[1], y, fmaf(cc.zc[2], z, cc.zc[3])));
+    al = fmaf(cc.al[0], x, fmaf(cc.al[1], y, fmaf(cc.al[2], z, cc.al[3])));
+    ah = fmaf(cc.ah[0], x, fmaf(cc.ah[1], y, fmaf(cc.ah[2], z, cc.ah[3])));
+  }
+  const float bl = fmaf(cc.bl[0], x, fmaf(cc.bl[1], y, fmaf(cc.bl[2], z, cc.bl[3])));
+  const float bh = fmaf(cc.bh[0], x, fmaf(cc.bh[1], y, fmaf(cc.bh[2], z, cc.bh[3])));
+  const bool front = Z > m;
+  const bool inside = front && al > m && ah < -m && bl > m && bh < -m;                       // surely in the image
+  const bool outside = (Z < -m) || (front && (al < -m || ah > m || bl < -m || bh > m));      // surely not
+  return lab == 1 ? !inside : !outside;
+}
+
+// ------------------------------------------------------------------------------------------
 // Shared-memory layout of one CTA.
 // ------------------------------------------------------------------------------------------
 template <typename CT>
@@ -244,6 +311,21 @@ struct alignas(16) TileBuf {
   CT z[kTile];
   int8_t lab[kTile];
 };
+
+// Self-contained record of a maybe-active point, queued per warp until 32 are pending.
+template <typename CT> struct Entry;
+template <> struct alignas(16) Entry<float> { float x, y, z; int lab; };
+template <> struct alignas(16) Entry<double> { double x, y, z; long long lab; };
+
+__device__ __forceinline__ void load4(const float* p, float o[4]) {
+  const float4 t = *reinterpret_cast<const float4*>(p);
+  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void load4(const double* p, double o[4]) {
+  const double2 a = *reinterpret_cast<const double2*>(p);
+  const double2 b = *reinterpret_cast<const double2*>(p + 2);
+  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+}
 
 struct LsSample {
   double x, value, gradient;
@@ -266,13 +348,20 @@ struct LMState {
   int ls_iter, evals, ls_steps, term;
 };
 
+constexpr int kSlice = kTile / kWarps;   // points of a tile owned by one warp
+constexpr int kGroup = 128;              // points a warp classifies per step (4 per lane)
+constexpr int kRing = 256;               // pending ring: < 32 carried + at most 128 appended per step
+
 template <typename CT, int P>
 struct Smem {
   TileBuf<CT> tile[kStages];
+  Entry<CT> list[kWarps][kRing];
   alignas(8) uint64_t full[kStages];
+  int done[kStages];                     // warps finished with a ring slot
   double red[kWarps][NAcc<P>::N];
   double tot[NAcc<P>::N];
   PoseConst pose;
+  ClassConst cls;
   Cam cam;
   LMState<P> lm;
   int problem;       // current problem id (broadcast)
@@ -282,6 +371,9 @@ struct Smem {
 // ------------------------------------------------------------------------------------------
 // One pass over a cloud: stages tiles, accumulates, block-reduces into sm.tot (all threads must
 // call).  `seq` is the CTA-lifetime count of consumed tiles (selects ring slot and phase).
+// Each warp owns a fixed slice of every tile and runs decoupled from the other warps: fp32
+// culling -> ordered compaction into its pending list -> exact fp64 evaluation of 32 pending
+// points at a time (all lanes busy).  The warp that finishes a ring slot last refills it.
 // ------------------------------------------------------------------------------------------
 template <typename CT>
 __device__ __forceinline__ void issue_tile(TileBuf<CT>* buf, uint64_t* bar, const CT* xyz_s, const int8_t* lab_s,
@@ -302,10 +394,14 @@ template <typename CT, int P>
 __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, int n_stride, int n,
                                uint32_t& seq) {
   constexpr int N = NAcc<P>::N;
+  constexpr int GPT = kSlice / kGroup;   // steps per tile
   const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const int ntiles = (n + kTile - 1) / kTile;
   if (tid == 0) {
     const int pre = ntiles < kStages ? ntiles : kStages;
+#pragma unroll 1
     for (int t = 0; t < pre; ++t) {
       const uint32_t q = seq + t;
       issue_tile<CT>(&sm.tile[q % kStages], &sm.full[q % kStages], xyz_s, lab_s, n_stride, n, t);
@@ -314,25 +410,67 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
   double acc[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) acc[j] = 0.0;
-  const Cam cam = sm.cam;
+  const Cam& cam = sm.cam;
   const PoseConst& pc = sm.pose;
+  const ClassConst& cc = sm.cls;
+  Entry<CT>* ring = sm.list[warp];
+  int head = 0, pending = 0;             // warp-uniform
 
-  for (int t = 0; t < ntiles; ++t) {
-    const uint32_t q = seq + t;
-    const int stage = q % kStages;
-    mbar_wait(&sm.full[stage], (q / kStages) & 1);
-    const TileBuf<CT>& tb = sm.tile[stage];
-    int cnt = n - t * kTile;
-    if (cnt > kTile) cnt = kTile;
-    for (int i = tid; i < cnt; i += kThreads) {
-      const int lab = tb.lab[i];
-      if (lab == 0 || lab == 1)
-        point_accumulate<P>((double)tb.x[i], (double)tb.y[i], (double)tb.z[i], lab, cam, pc, acc);
+  // One flat loop: steps 0 .. ntiles*GPT-1 classify 128 points each and drain full batches of 32;
+  // the extra last step only drains what is left (so the exact evaluation has ONE code instance).
+  const int nsteps = ntiles * GPT;
+#pragma unroll 1
+  for (int step = 0; step <= nsteps; ++step) {
+    int threshold = 1;
+    if (step < nsteps) {
+      threshold = 32;
+      const int t = step / GPT, g = step - t * GPT;
+      const uint32_t q = seq + t;
+      const int stage = q % kStages;
+      if (g == 0) mbar_wait(&sm.full[stage], (q / kStages) & 1);
+      const TileBuf<CT>& tb = sm.tile[stage];
+      int tile_cnt = n - t * kTile;
+      if (tile_cnt > kTile) tile_cnt = kTile;
+      const int i0 = warp * kSlice + g * kGroup + lane * 4;
+      CT px[4], py[4], pz[4];
+      load4(tb.x + i0, px);
+      load4(tb.y + i0, py);
+      load4(tb.z + i0, pz);
+      const int lab4 = *reinterpret_cast<const int*>(tb.lab + i0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int lab = (int)(int8_t)((lab4 >> (8 * j)) & 0xff);
+        const bool mb = (i0 + j < tile_cnt) && maybe_active<P>((float)px[j], (float)py[j], (float)pz[j], lab, cc);
+        const unsigned m = __ballot_sync(0xffffffffu, mb);
+        if (mb) {
+          Entry<CT> e;
+          e.x = px[j]; e.y = py[j]; e.z = pz[j]; e.lab = lab;
+          ring[(head + pending + __popc(m & lt_mask)) & (kRing - 1)] = e;
+        }
+        pending += __popc(m);
+      }
+      if (g == GPT - 1) {                // this warp is done with the ring slot
+        __syncwarp();
+        if (lane == 0) {
+          const int old = atomicAdd(&sm.done[stage], 1);
+          if (old == kWarps - 1) {       // last warp out refills it
+            sm.done[stage] = 0;
+            if (t + kStages < ntiles)
+              issue_tile<CT>(&sm.tile[stage], &sm.full[stage], xyz_s, lab_s, n_stride, n, t + kStages);
+          }
+        }
+      }
     }
-    __syncthreads();   // every thread is done with this ring slot
-    if (tid == 0 && t + kStages < ntiles) {
-      const uint32_t qn = q + kStages;
-      issue_tile<CT>(&sm.tile[qn % kStages], &sm.full[qn % kStages], xyz_s, lab_s, n_stride, n, t + kStages);
+#pragma unroll 1
+    while (pending >= threshold) {
+      __syncwarp();
+      const int take = pending < 32 ? pending : 32;
+      if (lane < take) {
+        const Entry<CT> e = ring[(head + lane) & (kRing - 1)];
+        point_accumulate<P>((double)e.x, (double)e.y, (double)e.z, (int)e.lab, cam, pc, acc);
+      }
+      head = (head + take) & (kRing - 1);
+      pending -= take;
     }
   }
   seq += ntiles;
@@ -345,7 +483,6 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     acc[j] = v;
   }
-  const int warp = tid >> 5, lane = tid & 31;
   if (lane == 0) {
 #pragma unroll
     for (int j = 0; j < N; ++j) sm.red[warp][j] = acc[j];
@@ -364,7 +501,8 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
 // Trust-region control flow (thread 0 only).
 // ------------------------------------------------------------------------------------------
 template <int P>
-__device__ void project_plus(const LMState<P>& st, const double* x, const double* d, double a, double* out) {
+__device__ __noinline__ void project_plus(const LMState<P>& st, const double* x, const double* d, double a, double* out) {
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) {
     double v = x[j] + a * d[j];
     v = fmax(v, st.lb[j]);
@@ -374,8 +512,9 @@ __device__ void project_plus(const LMState<P>& st, const double* x, const double
 }
 
 template <int P>
-__device__ double grad_max_norm(const LMState<P>& st, const double* x, const double* g) {
+__device__ __noinline__ double grad_max_norm(const LMState<P>& st, const double* x, const double* g) {
   double mx = 0.0;
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) {
     double v = x[j] - g[j];
     v = fmax(v, st.lb[j]);
@@ -387,11 +526,14 @@ __device__ double grad_max_norm(const LMState<P>& st, const double* x, const dou
 
 // Solve (As + diag(d2)) y = gs by Cholesky; As given as packed upper triangle.  false if not SPD.
 template <int P>
-__device__ bool chol_solve(const double* As, const double* d2, const double* gs, double* y) {
+__device__ __noinline__ bool chol_solve(const double* As, const double* d2, const double* gs, double* y) {
   double L[P][P];
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) {
+    #pragma unroll 1
     for (int i = j; i < P; ++i) {
       double s = As[tri(P, j, i)] + (i == j ? d2[j] : 0.0);
+      #pragma unroll 1
       for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
       if (i == j) {
         if (!(s > 0.0)) return false;
@@ -402,13 +544,17 @@ __device__ bool chol_solve(const double* As, const double* d2, const double* gs,
     }
   }
   double z[P];
+  #pragma unroll 1
   for (int i = 0; i < P; ++i) {
     double s = gs[i];
+    #pragma unroll 1
     for (int k = 0; k < i; ++k) s -= L[i][k] * z[k];
     z[i] = s / L[i][i];
   }
+  #pragma unroll 1
   for (int i = P - 1; i >= 0; --i) {
     double s = z[i];
+    #pragma unroll 1
     for (int k = i + 1; k < P; ++k) s -= L[k][i] * y[k];
     y[i] = s / L[i][i];
   }
@@ -417,22 +563,26 @@ __device__ bool chol_solve(const double* As, const double* d2, const double* gs,
 
 __device__ double poly_eval(const double* p, int n, double x) {   // n coefficients, highest first
   double v = 0.0;
+  #pragma unroll 1
   for (int i = 0; i < n; ++i) v = v * x + p[i];
   return v;
 }
 
 __device__ double ipow(double x, int k) {
   double v = 1.0;
+  #pragma unroll 1
   for (int i = 0; i < k; ++i) v *= x;
   return v;
 }
 
 // Real parts of all roots of p (n coefficients, highest first; n - 1 <= 4).
-__device__ int poly_roots_real(const double* pin, int n, double* roots) {
+__device__ __noinline__ int poly_roots_real(const double* pin, int n, double* roots) {
   double p[6];
   int lead = 0;
+  #pragma unroll 1
   while (lead < n && pin[lead] == 0.0) ++lead;
   const int m = n - lead;
+  #pragma unroll 1
   for (int i = 0; i < m; ++i) p[i] = pin[lead + i];
   const int deg = m - 1;
   if (deg <= 0) return 0;
@@ -450,24 +600,31 @@ __device__ int poly_roots_real(const double* pin, int n, double* roots) {
   // Durand-Kerner on the monic polynomial
   double zr[5], zi[5], c[6];
   double maxc = 0.0;
+  #pragma unroll 1
   for (int i = 0; i <= deg; ++i) c[i] = p[i] / p[0];
+  #pragma unroll 1
   for (int i = 1; i <= deg; ++i) maxc = fmax(maxc, fabs(c[i]));
   const double radius = 1.0 + maxc;
+  #pragma unroll 1
   for (int i = 0; i < deg; ++i) {
     double s, co;
     sincos(2.0 * 3.14159265358979323846 * i / deg + 0.4, &s, &co);
     zr[i] = 0.5 * radius * co; zi[i] = 0.5 * radius * s;
   }
+  #pragma unroll 1
   for (int it = 0; it < 500; ++it) {
     double change = 0.0;
+    #pragma unroll 1
     for (int i = 0; i < deg; ++i) {
       double nr = 0.0, ni = 0.0;
+      #pragma unroll 1
       for (int k = 0; k <= deg; ++k) {
         const double tr = nr * zr[i] - ni * zi[i] + c[k];
         const double ti = nr * zi[i] + ni * zr[i];
         nr = tr; ni = ti;
       }
       double dr = 1.0, di = 0.0;
+      #pragma unroll 1
       for (int j = 0; j < deg; ++j) if (j != i) {
         const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
         const double tr = dr * er - di * ei, ti = dr * ei + di * er;
@@ -481,56 +638,70 @@ __device__ int poly_roots_real(const double* pin, int n, double* roots) {
     }
     if (change < 1e-15 * radius) break;
   }
+  #pragma unroll 1
   for (int i = 0; i < deg; ++i) roots[i] = zr[i];
   return deg;
 }
 
 // Step size minimising the polynomial that interpolates the line-search samples over
 // [xmin, xmax] (cubic interpolation: values and gradients of lower / current / previous).
-__device__ double interpolating_min_step(const LsSample& lower, const LsSample& previous, const LsSample& current,
+__device__ __noinline__ double interpolating_min_step(const LsSample& lower, const LsSample& previous, const LsSample& current,
                                          double xmin, double xmax) {
   if (!current.value_valid) return fmin(fmax(current.x * 0.5, xmin), xmax);
   const LsSample* s[3] = {&lower, &current, &previous};
   const int ns = previous.value_valid ? 3 : 2;
   int nc = 0;
+  #pragma unroll 1
   for (int i = 0; i < ns; ++i) { if (s[i]->value_valid) ++nc; if (s[i]->gradient_valid) ++nc; }
   const int deg = nc - 1;
   double M[6][6], rhs[6], poly[6];
+  #pragma unroll 1
   for (int i = 0; i < 6; ++i) { rhs[i] = 0; poly[i] = 0; for (int j = 0; j < 6; ++j) M[i][j] = 0; }
   int row = 0;
+  #pragma unroll 1
   for (int i = 0; i < ns; ++i) {
     if (s[i]->value_valid) {
+      #pragma unroll 1
       for (int j = 0; j <= deg; ++j) M[row][j] = ipow(s[i]->x, deg - j);
       rhs[row] = s[i]->value; ++row;
     }
     if (s[i]->gradient_valid) {
+      #pragma unroll 1
       for (int j = 0; j < deg; ++j) M[row][j] = (deg - j) * ipow(s[i]->x, deg - j - 1);
       rhs[row] = s[i]->gradient; ++row;
     }
   }
   // full-pivot elimination
   int perm[6];
+  #pragma unroll 1
   for (int i = 0; i < nc; ++i) perm[i] = i;
+  #pragma unroll 1
   for (int k = 0; k < nc; ++k) {
     int pr = k, pcv = k; double best = -1.0;
+    #pragma unroll 1
     for (int i = k; i < nc; ++i) for (int j = k; j < nc; ++j)
       if (fabs(M[i][j]) > best) { best = fabs(M[i][j]); pr = i; pcv = j; }
     if (best == 0.0) { for (int i = k; i < nc; ++i) rhs[i] = 0.0; break; }
     if (pr != k) { for (int j = 0; j < nc; ++j) { double t = M[pr][j]; M[pr][j] = M[k][j]; M[k][j] = t; } double t = rhs[pr]; rhs[pr] = rhs[k]; rhs[k] = t; }
     if (pcv != k) { for (int i = 0; i < nc; ++i) { double t = M[i][pcv]; M[i][pcv] = M[i][k]; M[i][k] = t; } int t = perm[pcv]; perm[pcv] = perm[k]; perm[k] = t; }
+    #pragma unroll 1
     for (int i = k + 1; i < nc; ++i) {
       const double f = M[i][k] / M[k][k];
+      #pragma unroll 1
       for (int j = k; j < nc; ++j) M[i][j] -= f * M[k][j];
       rhs[i] -= f * rhs[k];
     }
   }
   double z[6];
+  #pragma unroll 1
   for (int k = nc - 1; k >= 0; --k) {
     if (M[k][k] == 0.0) { z[k] = 0.0; continue; }
     double sacc = rhs[k];
+    #pragma unroll 1
     for (int j = k + 1; j < nc; ++j) sacc -= M[k][j] * z[j];
     z[k] = sacc / M[k][k];
   }
+  #pragma unroll 1
   for (int k = 0; k < nc; ++k) poly[perm[k]] = z[k];
 
   double best_x = (xmin + xmax) / 2.0;
@@ -541,8 +712,10 @@ __device__ double interpolating_min_step(const LsSample& lower, const LsSample& 
   if (vmax < best_v) { best_v = vmax; best_x = xmax; }
   if (nc <= 2) return best_x;
   double der[6], roots[5];
+  #pragma unroll 1
   for (int j = 0; j < deg; ++j) der[j] = (deg - j) * poly[j];
   const int nr = poly_roots_real(der, deg, roots);
+  #pragma unroll 1
   for (int i = 0; i < nr; ++i) {
     if (roots[i] < xmin || roots[i] > xmax) continue;
     const double v = poly_eval(poly, nc, roots[i]);
@@ -555,7 +728,7 @@ enum { LM_DONE = 0, LM_EVAL = 1 };
 
 // Starts the next trust-region iteration(s) until an evaluation is needed or the solve ends.
 template <int P>
-__device__ int lm_next_step(LMState<P>& st) {
+__device__ __noinline__ int lm_next_step(LMState<P>& st) {
   constexpr int NA = NAcc<P>::NA;
   for (;;) {
     if (st.iteration >= st.max_iter) { st.term = 3; return LM_DONE; }
@@ -565,26 +738,33 @@ __device__ int lm_next_step(LMState<P>& st) {
     st.step_ok = 0;
 
     double As[NA], gs[P], d2[P], y[P];
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) {
       gs[j] = st.g[j] * st.scale[j];
+      #pragma unroll 1
       for (int k = j; k < P; ++k) As[tri(P, j, k)] = st.A[tri(P, j, k)] * st.scale[j] * st.scale[k];
     }
     if (!st.reuse_diag)
+      #pragma unroll 1
       for (int j = 0; j < P; ++j) st.diag[j] = fmin(fmax(As[tri(P, j, j)], 1e-6), 1e32);
     st.reuse_diag = 1;
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) { const double l = sqrt(st.diag[j] / st.radius); d2[j] = l * l; }
     bool ok = chol_solve<P>(As, d2, gs, y);
     double mcc = 0.0;
     if (ok) {
       // model cost change = -step^T gs - 1/2 step^T As step, step = -y
       double quad = 0.0, lin = 0.0;
+      #pragma unroll 1
       for (int j = 0; j < P; ++j) {
         st.step[j] = -y[j];
         if (!isfinite(st.step[j])) ok = false;
       }
+      #pragma unroll 1
       for (int j = 0; j < P; ++j) {
         lin += st.step[j] * gs[j];
         double rowsum = 0.0;
+        #pragma unroll 1
         for (int k = 0; k < P; ++k) rowsum += As[j <= k ? tri(P, j, k) : tri(P, k, j)] * st.step[k];
         quad += st.step[j] * rowsum;
       }
@@ -599,6 +779,7 @@ __device__ int lm_next_step(LMState<P>& st) {
     st.invalid = 0;
     st.mcc = mcc;
     double gd = 0.0, dmax = 0.0;
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) {
       st.delta[j] = st.step[j] * st.scale[j];
       gd += st.g[j] * st.delta[j];
@@ -616,19 +797,22 @@ __device__ int lm_next_step(LMState<P>& st) {
 }
 
 template <int P>
-__device__ int lm_after_candidate(LMState<P>& st, const double* tot) {
+__device__ __noinline__ int lm_after_candidate(LMState<P>& st, const double* tot) {
   constexpr int NA = NAcc<P>::NA;
   const double ccost = tot[0];
   double sn = 0.0;
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) sn += (st.x[j] - st.xt[j]) * (st.x[j] - st.xt[j]);
   if (sqrt(sn) <= 1e-8 * (st.x_norm + 1e-8)) { st.term = 1; return LM_DONE; }
   if (fabs(st.cost - ccost) <= 1e-6 * st.cost) { st.term = 2; return LM_DONE; }
   const double rho = (st.cost - ccost) / st.mcc;
   if (rho > 1e-3) {
     double xn = 0.0;
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) { st.x[j] = st.xt[j]; xn += st.x[j] * st.x[j]; st.g[j] = tot[1 + j]; }
     st.x_norm = sqrt(xn);
     st.cost = ccost;
+    #pragma unroll 1
     for (int j = 0; j < NA; ++j) st.A[j] = tot[1 + P + j];
     st.grad_max = grad_max_norm<P>(st, st.x, st.g);
     const double t = 2.0 * rho - 1.0;
@@ -652,8 +836,11 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
   ++st.evals;
   if (st.phase == 0) {
     st.cost = tot[0];
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) st.g[j] = tot[1 + j];
+    #pragma unroll 1
     for (int j = 0; j < NA; ++j) st.A[j] = tot[1 + P + j];
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) st.scale[j] = 1.0 / (1.0 + sqrt(st.A[tri(P, j, j)]));
     st.grad_max = grad_max_norm<P>(st, st.x, st.g);
     st.step_ok = 1;
@@ -664,11 +851,13 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
     cur.value = tot[0];
     cur.value_valid = isfinite(cur.value) ? 1 : 0;
     double gr = 0.0;
+    #pragma unroll 1
     for (int j = 0; j < P; ++j) gr += st.delta[j] * tot[1 + j];
     cur.gradient = gr;
     cur.gradient_valid = (cur.value_valid && isfinite(gr)) ? 1 : 0;
     const bool armijo_ok = cur.value_valid && !(cur.value > st.cost + 1e-4 * st.gd * cur.x);
     if (armijo_ok) {
+      #pragma unroll 1
       for (int j = 0; j < P; ++j) st.delta[j] *= cur.x;
       return lm_after_candidate<P>(st, tot);      // candidate == this sample, bit for bit
     }
@@ -690,6 +879,7 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
     cur.x = a;
     {
       double sd[P];
+      #pragma unroll 1
       for (int j = 0; j < P; ++j) sd[j] = a * st.delta[j];
       project_plus<P>(st, st.x, sd, 1.0, st.xt);
     }
@@ -700,19 +890,24 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
 
 // Returns LM_EVAL (st.xt set) or LM_DONE (infeasible start).
 template <int P>
-__device__ int lm_begin(LMState<P>& st, const double* init4, const double* lb3, const double* ub3, int max_iter) {
+__device__ __noinline__ int lm_begin(LMState<P>& st, const double* init4, const double* lb3, const double* ub3, int max_iter) {
   constexpr int toff = P - 3;
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) { st.lb[j] = -DBL_MAX; st.ub[j] = DBL_MAX; st.x[j] = 0.0; }
+  #pragma unroll 1
   for (int k = 0; k < 3; ++k) { st.lb[toff + k] = lb3[k]; st.ub[toff + k] = ub3[k]; st.x[toff + k] = init4[1 + k]; }
   st.x[P == 4 ? 0 : 1] = init4[0];        // registration.cpp:34-50
   st.max_iter = max_iter;
   st.iteration = 0; st.evals = 0; st.ls_steps = 0; st.term = -1; st.invalid = 0;
   st.radius = 1e4; st.dec = 2.0; st.reuse_diag = 0; st.step_ok = 1; st.phase = 0;
   st.cost = 0.0; st.grad_max = 0.0;
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) st.g[j] = 0.0;
+  #pragma unroll 1
   for (int j = 0; j < P; ++j)
     if (st.x[j] < st.lb[j] || st.x[j] > st.ub[j]) { st.term = 6; return LM_DONE; }
   double xn = 0.0;
+  #pragma unroll 1
   for (int j = 0; j < P; ++j) { st.xt[j] = st.x[j]; xn += st.x[j] * st.x[j]; }
   st.x_norm = sqrt(xn);
   return LM_EVAL;
@@ -741,12 +936,12 @@ struct SolveArgs {
 };
 
 template <typename CT, int P>
-__global__ void __launch_bounds__(kThreads) frustum_solve_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(kThreads, (P == 4) ? 4 : 3) frustum_solve_kernel(SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); sm.done[s] = 0; }
     mbar_fence_init();
   }
   __syncthreads();
@@ -766,7 +961,7 @@ __global__ void __launch_bounds__(kThreads) frustum_solve_kernel(SolveArgs a) {
       make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &sm.cam);
       const int rc = lm_begin<P>(sm.lm, a.init + (size_t)prob * 4, a.lb, a.ub, a.max_iter);
       sm.go = rc;
-      if (rc == LM_EVAL) make_pose<P>(sm.lm.xt, &sm.pose);
+      if (rc == LM_EVAL) { make_pose<P>(sm.lm.xt, &sm.pose); make_class(sm.pose, sm.cam, &sm.cls); }
     }
     __syncthreads();
     while (sm.go == LM_EVAL) {
@@ -774,7 +969,7 @@ __global__ void __launch_bounds__(kThreads) frustum_solve_kernel(SolveArgs a) {
       if (tid == 0) {
         const int rc = lm_consume<P>(sm.lm, sm.tot);
         sm.go = rc;
-        if (rc == LM_EVAL) make_pose<P>(sm.lm.xt, &sm.pose);
+        if (rc == LM_EVAL) { make_pose<P>(sm.lm.xt, &sm.pose); make_class(sm.pose, sm.cam, &sm.cls); }
       }
       __syncthreads();
     }
@@ -843,10 +1038,11 @@ __global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xy
   const int tid = threadIdx.x;
   const int s = blockIdx.x;
   if (tid == 0) {
-    for (int k = 0; k < kStages; ++k) mbar_init(&sm.full[k], 1);
+    for (int k = 0; k < kStages; ++k) { mbar_init(&sm.full[k], 1); sm.done[k] = 0; }
     mbar_fence_init();
     make_cam(K9 + (size_t)s * 9, H, W, &sm.cam);
     make_pose<P>(x + (size_t)s * 6, &sm.pose);
+    make_class(sm.pose, sm.cam, &sm.cls);
   }
   __syncthreads();
   uint32_t seq = 0;

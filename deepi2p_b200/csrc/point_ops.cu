@@ -139,7 +139,7 @@ int index_max_forward(const float* data, const int32_t* index, int32_t* out, int
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (N % 4 == 0) && ((uintptr_t)data % 16 == 0) && ((uintptr_t)index % 16 == 0);
   const size_t per_c = (size_t)K * 12;
-  const size_t limit = 200 * 1024;
+  const size_t limit = 227 * 1024;
   int cpb = 4;
   while (cpb > 1 && per_c * cpb > limit) cpb >>= 1;
   DIB_REQUIRE(per_c * cpb <= limit, "K=%d too large for the shared-memory segment table", K);

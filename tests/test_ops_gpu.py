@@ -27,7 +27,7 @@ def run_ball_query(dist, radius, K):
 
 
 @pytest.mark.parametrize("B,C,N,K", [(2, 5, 1000, 16), (3, 32, 20480, 128), (1, 1, 7, 3), (2, 7, 1023, 64),
-                                     (1, 3, 4096, 4000), (1, 2, 513, 20000)])
+                                     (1, 3, 4096, 4000), (1, 2, 513, 19000)])
 def test_index_max_random(cuda, B, C, N, K):
     data, index = syn.make_index_max_inputs(B * 1000 + C, B, C, N, K)
     np.testing.assert_array_equal(run_index_max(data, index, K), oracle.index_max(data, index, K))
