@@ -13,6 +13,7 @@ _lib = None
 EXPORTS = (
     "dib_abi_version", "dib_last_error", "dib_device_sm_count",
     "frustum_solve_workspace_bytes", "frustum_solve_batch_f32", "frustum_solve_batch_f64",
+    "frustum_evaluate_workspace_bytes",
     "frustum_evaluate_f32", "frustum_evaluate_f64", "frustum_residuals_f32", "frustum_residuals_f64",
     "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32",
     "index_max_forward", "ball_query_forward",
@@ -47,13 +48,15 @@ def load():
     lib.dib_last_error.restype = _c.c_char_p
     lib.dib_device_sm_count.restype = i32
     lib.frustum_solve_workspace_bytes.restype = sz
-    lib.frustum_solve_workspace_bytes.argtypes = [i32, i32]
+    lib.frustum_solve_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.frustum_evaluate_workspace_bytes.restype = sz
+    lib.frustum_evaluate_workspace_bytes.argtypes = [i32, i32]
     solve_args = [vp, vp, vp, i32, vp, vp, vp, vp, f64, f64, i32, i32, i32, i32,
                   vp, vp, vp, vp, vp, vp, vp, sz, vp]
     for name in ("frustum_solve_batch_f32", "frustum_solve_batch_f64"):
         getattr(lib, name).restype = i32
         getattr(lib, name).argtypes = solve_args
-    eval_args = [vp, vp, vp, i32, vp, vp, f64, f64, i32, i32, vp, vp, vp, vp]
+    eval_args = [vp, vp, vp, i32, vp, vp, f64, f64, i32, i32, vp, vp, vp, vp, sz, vp]
     for name in ("frustum_evaluate_f32", "frustum_evaluate_f64"):
         getattr(lib, name).restype = i32
         getattr(lib, name).argtypes = eval_args
@@ -64,7 +67,7 @@ def load():
     lib.frustum_prepare_workspace_bytes.restype = sz
     lib.frustum_prepare_workspace_bytes.argtypes = [i32, i32]
     lib.frustum_prepare_batch_f32.restype = i32
-    lib.frustum_prepare_batch_f32.argtypes = [vp, vp, i32, i32, i32, i32, _c.c_uint64, f64, f64,
+    lib.frustum_prepare_batch_f32.argtypes = [vp, vp, i32, i32, i32, i32, _c.c_uint64, f64, f64, i32,
                                               vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.index_max_forward.restype = i32
     lib.index_max_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]

@@ -46,7 +46,8 @@ def build(force=False, verbose=False, extra=()):
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, "-o", LIB + ".tmp", *srcs]
+    env_extra = os.environ.get("DIB_NVCC_EXTRA", "").split()
+    cmd = [nvcc_path(), *NVCC_FLAGS, *extra, *env_extra, "-o", LIB + ".tmp", *srcs]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

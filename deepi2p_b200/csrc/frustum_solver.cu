@@ -30,10 +30,18 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-constexpr int kThreads = 128;           // threads per problem (CTA)
+#ifndef DIB_THREADS
+#define DIB_THREADS 64
+#endif
+#ifndef DIB_MINBLOCKS4
+#define DIB_MINBLOCKS4 8
+#endif
+#ifndef DIB_MINBLOCKS6
+#define DIB_MINBLOCKS6 6
+#endif
+constexpr int kThreads = DIB_THREADS;   // threads per problem (CTA)
 constexpr int kWarps = kThreads / 32;
-constexpr int kTile = 1024;             // points per staged tile
-constexpr int kStages = 3;              // bulk-copy ring depth
+
 
 struct Cam {
   double fx, fy, cx, cy, W1, H1, hW, hH;
@@ -235,6 +243,150 @@ __device__ __forceinline__ void point_accumulate(double px, double py, double pz
 }
 
 // ------------------------------------------------------------------------------------------
+// Branch-free evaluators used by the solver's hot loop.  Batches are homogeneous in the label and
+// every lane evaluates two points, so that two independent dependency chains are in flight per
+// lane.  `valid == false` (padding lane) and exact-inactive points contribute exactly zero.
+// ------------------------------------------------------------------------------------------
+template <int P>
+struct Proj {
+  double X, Y, Z, iz, u, v;
+  double dX[P - 3], dY[P - 3], dZ[P - 3];
+};
+
+template <int P>
+__device__ __forceinline__ void project_point(double px, double py, double pz, bool valid, const Cam& cam,
+                                              const PoseConst& pc, Proj<P>& o) {
+  constexpr int NR = P - 3;
+  if (!valid) { px = 0.0; py = 0.0; pz = 0.0; }
+  const double rx = fma(pc.R[0], px, fma(pc.R[1], py, pc.R[2] * pz));
+  const double ry_ = fma(pc.R[3], px, fma(pc.R[4], py, pc.R[5] * pz));
+  const double rz = fma(pc.R[6], px, fma(pc.R[7], py, pc.R[8] * pz));
+  o.X = rx + pc.t[0]; o.Y = ry_ + pc.t[1]; o.Z = rz + pc.t[2];
+  const double zs = (valid && o.Z != 0.0) ? o.Z : 1.0;     // keeps masked lanes finite
+  o.iz = 1.0 / zs;
+  o.u = fma(cam.fx * o.X, o.iz, cam.cx);
+  o.v = fma(cam.fy * o.Y, o.iz, cam.cy);
+  if (P == 4) {
+    o.dX[0] = fma(-pc.sD, px, pc.cD * pz);
+    o.dY[0] = 0.0;
+    o.dZ[0] = -fma(pc.cD, px, pc.sD * pz);
+  } else {
+    const double a = pc.small ? px : rx, b = pc.small ? py : ry_, c = pc.small ? pz : rz;
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      o.dX[k] = c * pc.Jl[3 + k] - b * pc.Jl[6 + k];
+      o.dY[k] = a * pc.Jl[6 + k] - c * pc.Jl[k];
+      o.dZ[k] = b * pc.Jl[k] - a * pc.Jl[3 + k];
+    }
+  }
+}
+
+// label 0 ("should be outside", registration_3d.hpp:34-68): one dense row.
+template <int P>
+struct Out0 {
+  double w, r, s1;      // corrector weight (0 if inactive), residual, 1 + s
+  double J[P];
+};
+
+template <int P>
+__device__ __forceinline__ void eval_outside(double px, double py, double pz, bool valid, const Cam& cam,
+                                             const PoseConst& pc, Out0<P>& o) {
+  constexpr int NR = P - 3;
+  Proj<P> q;
+  project_point<P>(px, py, pz, valid, cam, pc, q);
+  const double du_ = q.u - cam.hW, dv_ = q.v - cam.hH;
+  const double xd = cam.hW - fabs(du_), yd = cam.hH - fabs(dv_);
+  const bool act = valid && q.Z > 0.0 && xd > 0.0 && yd > 0.0;
+  const double su = (du_ < 0.0) ? 1.0 : -1.0;      // -sgn(u - W1/2), sgn(0) = +1
+  const double sv = (dv_ < 0.0) ? 1.0 : -1.0;
+  o.r = act ? xd + yd : 0.0;
+  o.s1 = fma(o.r, o.r, 1.0);
+  o.w = act ? 1.0 / o.s1 : 0.0;
+  const double au = su * (cam.fx * q.iz), bu = su * ((q.u - cam.cx) * q.iz);
+  const double av = sv * (cam.fy * q.iz), bv = sv * ((q.v - cam.cy) * q.iz);
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    double j = au * q.dX[k] - (bu + bv) * q.dZ[k];
+    if (P != 4) j = fma(av, q.dY[k], j);
+    o.J[k] = j;
+  }
+  o.J[NR] = au; o.J[NR + 1] = av; o.J[NR + 2] = -(bu + bv);
+}
+
+// label 1 ("should be inside", registration_3d.hpp:105-127): three sparse rows
+//   JU = su dU (no ty entry), JV = sv dV (no tx entry), JZ = sz dZ (rot and tz entries only).
+template <int P>
+struct Out1 {
+  double w, r0, r1, r2, s1;
+  double JU[P], JV[P], JZ[P];
+};
+
+template <int P>
+__device__ __forceinline__ void eval_inside(double px, double py, double pz, bool valid, const Cam& cam,
+                                            const PoseConst& pc, Out1<P>& o) {
+  constexpr int NR = P - 3;
+  Proj<P> q;
+  project_point<P>(px, py, pz, valid, cam, pc, q);
+  const double a0 = -q.u, b0 = q.u - cam.W1;
+  const double a1 = -q.v, b1 = q.v - cam.H1;
+  double su = (a0 < 0.0 ? 0.0 : -1.0) + (b0 < 0.0 ? 0.0 : 1.0);
+  double sv = (a1 < 0.0 ? 0.0 : -1.0) + (b1 < 0.0 ? 0.0 : 1.0);
+  double sz = (-q.Z < 0.0) ? 0.0 : -100.0;
+  o.r0 = (a0 < 0.0 ? 0.0 : a0) + (b0 < 0.0 ? 0.0 : b0);
+  o.r1 = (a1 < 0.0 ? 0.0 : a1) + (b1 < 0.0 ? 0.0 : b1);
+  o.r2 = (-q.Z < 0.0 ? 0.0 : -q.Z) * 100.0;
+  if (!valid) { su = 0.0; sv = 0.0; sz = 0.0; o.r0 = 0.0; o.r1 = 0.0; o.r2 = 0.0; }
+  o.s1 = fma(o.r0, o.r0, fma(o.r1, o.r1, fma(o.r2, o.r2, 1.0)));
+  o.w = 1.0 / o.s1;
+  const double au = su * (cam.fx * q.iz), bu = su * ((q.u - cam.cx) * q.iz);
+  const double av = sv * (cam.fy * q.iz), bv = sv * ((q.v - cam.cy) * q.iz);
+#pragma unroll
+  for (int k = 0; k < NR; ++k) {
+    o.JU[k] = au * q.dX[k] - bu * q.dZ[k];
+    o.JV[k] = (P == 4) ? -bv * q.dZ[k] : av * q.dY[k] - bv * q.dZ[k];
+    o.JZ[k] = sz * q.dZ[k];
+  }
+  o.JU[NR] = au;  o.JU[NR + 1] = 0.0; o.JU[NR + 2] = -bu;
+  o.JV[NR] = 0.0; o.JV[NR + 1] = av;  o.JV[NR + 2] = -bv;
+  o.JZ[NR] = 0.0; o.JZ[NR + 1] = 0.0; o.JZ[NR + 2] = sz;
+}
+
+// rank-1 update restricted to the entries of J that can be non-zero (compile-time MASK).
+template <int P, unsigned MASK>
+__device__ __forceinline__ void rank1_masked(double* acc, const double* J, double w, double r) {
+  const double wr = w * r;
+#pragma unroll
+  for (int j = 0; j < P; ++j) {
+    if ((MASK >> j) & 1u) {
+      acc[1 + j] = fma(wr, J[j], acc[1 + j]);
+      const double wj = w * J[j];
+#pragma unroll
+      for (int k = j; k < P; ++k)
+        if ((MASK >> k) & 1u) acc[1 + P + tri(P, j, k)] = fma(wj, J[k], acc[1 + P + tri(P, j, k)]);
+    }
+  }
+}
+
+template <int P>
+__device__ __forceinline__ void accumulate_inside(double* acc, const Out1<P>& o) {
+  constexpr int NR = P - 3;
+  constexpr unsigned ROT = (1u << NR) - 1u;
+  rank1_masked<P, ROT | (1u << NR) | (1u << (NR + 2))>(acc, o.JU, o.w, o.r0);
+  rank1_masked<P, ROT | (1u << (NR + 1)) | (1u << (NR + 2))>(acc, o.JV, o.w, o.r1);
+  rank1_masked<P, ROT | (1u << (NR + 2))>(acc, o.JZ, o.w, o.r2);
+}
+
+// Running product of (1 + s) kept as mantissa in [1,2) x 2^expo: sum log(1+s) = log(prod) + expo ln 2.
+__device__ __forceinline__ void renorm_product(double& prod, int& expo) {
+  const int hi = __double2hiint(prod);
+  const int e = ((hi >> 20) & 0x7ff) - 1023;
+  if (e != 1024) {                       // leave inf / NaN alone so that they propagate
+    expo += e;
+    prod = __hiloint2double(hi - (e << 20), __double2loint(prod));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Conservative fp32 activity test.  Most points contribute exactly zero to cost, gradient and
 // J^T J at a given pose (an "outside" point that projects outside, an "inside" point that
 // projects inside).  Each test  u > 0, u < W1, v > 0, v < H1, Z > 0  is, for Z > 0, the sign of
@@ -258,24 +410,33 @@ __device__ __noinline__ void make_class(const PoseConst& pc, const Cam& cam, Cla
   const double kx[5] = {0.0, cam.fx, cam.fx, 0.0, 0.0};
   const double ky[5] = {0.0, 0.0, 0.0, cam.fy, cam.fy};
   const double kz[5] = {1.0, cam.cx, cam.cx - cam.W1, cam.cy, cam.cy - cam.H1};
+  double R[9], t[3];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) R[j] = pc.R[j];
+#pragma unroll
+  for (int j = 0; j < 3; ++j) t[j] = pc.t[j];
   float* out = cc->zc;                       // zc, al, ah, bl, bh are contiguous float[4]
   double amax = 0.0, cmax = 0.0;
-  bool finite = true;
-#pragma unroll 1
+  float fsum = 0.0f;                         // stays finite iff every coefficient is
+#pragma unroll
   for (int f = 0; f < 5; ++f) {
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-      const double c = (j < 3) ? kx[f] * pc.R[j] + ky[f] * pc.R[3 + j] + kz[f] * pc.R[6 + j]
-                               : kx[f] * pc.t[0] + ky[f] * pc.t[1] + kz[f] * pc.t[2];
-      if (j < 3) amax = fmax(amax, fabs(c)); else cmax = fmax(cmax, fabs(c));
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      const double c = fma(kx[f], R[j], fma(ky[f], R[3 + j], kz[f] * R[6 + j]));
+      amax = fmax(amax, fabs(c));
       const float cf = (float)c;
-      if (!isfinite(cf)) finite = false;
+      fsum += fabsf(cf);
       out[4 * f + j] = cf;
     }
+    const double c3 = fma(kx[f], t[0], fma(ky[f], t[1], kz[f] * t[2]));
+    cmax = fmax(cmax, fabs(c3));
+    const float c3f = (float)c3;
+    fsum += fabsf(c3f);
+    out[4 * f + 3] = c3f;
   }
   cc->G = (float)(gamma * amax * 1.0000002);
   cc->G0 = (float)(gamma * cmax * 1.0000002) + 1e-30f;
-  cc->enabled = (finite && isfinite(cc->G) && isfinite(cc->G0)) ? 1 : 0;
+  cc->enabled = (isfinite(fsum) && isfinite(cc->G) && isfinite(cc->G0)) ? 1 : 0;
 }
 
 template <int P>
@@ -302,30 +463,92 @@ __device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab,
 }
 
 // ------------------------------------------------------------------------------------------
+// Box table.  The cloud of a sample is static over all of its (inits x evaluations) passes, so
+// each group of 32 consecutive points gets an axis-aligned bounding box once per launch
+// (frustum_boxes_kernel).  A linear form over a box ranges over  f(centre) +- sum |coef| half,
+// so one lane decides a whole group against the five forms; only undecided groups are ever
+// loaded point by point.  (frustum_prepare_batch sorts points by (label, Morton cell) so that
+// groups are spatially compact and label-pure; unsorted clouds still work, they just cull less.)
+//
+// Global layout per sample: rounds x [8 fields][kThreads] floats, group id of slot (round r, warp
+// w, lane l) = r * kThreads + l * kWarps + w  -- neighbouring groups are dealt round-robin to the
+// warps (load balance) while each warp reads consecutive words (no bank conflicts).
+// Fields: cx cy cz hx hy hz flags(bit0: has label 0, bit1: has label 1) pad.
+// ------------------------------------------------------------------------------------------
+constexpr int kBoxFields = 8;
+constexpr int kBoxRoundFloats = kBoxFields * kThreads;
+#ifndef DIB_BOX_ROUNDS
+#define DIB_BOX_ROUNDS 8
+#endif
+#ifndef DIB_BOX_SMEM
+#define DIB_BOX_SMEM 0                        // 1: table bulk-copied (TMA engine) into shared memory per problem; 0: read via L1/L2
+                                              // (measured faster on B200: profiles/r01_sweep_build_params.jsonl)
+#endif
+constexpr int kBoxRounds = DIB_BOX_SMEM ? DIB_BOX_ROUNDS : 1;   // rounds resident in shared memory (x kThreads x 32 points)
+
+__host__ __device__ inline int box_rounds(int n) { return (((n + 31) >> 5) + kThreads - 1) / kThreads; }
+
+template <typename CT>
+__global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict__ xyz,
+                                                            const int8_t* __restrict__ label,
+                                                            const int32_t* __restrict__ n_pts, int n_stride,
+                                                            int rounds_max, float* __restrict__ table) {
+  const int s = blockIdx.y;
+  const int lane = threadIdx.x & 31;
+  const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gid >= rounds_max * kThreads) return;
+  const int n = n_pts ? n_pts[s] : n_stride;
+  const int i = gid * 32 + lane;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  int lab = -1;
+  if (i < n) {
+    lab = label[(size_t)s * n_stride + i];
+    if (lab == 0 || lab == 1) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double v = (double)xyz[((size_t)s * 3 + c) * n_stride + i];
+        lo[c] = v; hi[c] = v;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[c] = fmin(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+      hi[c] = fmax(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+    }
+  const unsigned m0 = __ballot_sync(0xffffffffu, lab == 0), m1 = __ballot_sync(0xffffffffu, lab == 1);
+  if (lane == 0) {
+    const int r = gid / kThreads, q = gid % kThreads;
+    const int w = q % kWarps, l = q / kWarps;
+    float* rec = table + ((size_t)s * rounds_max + r) * kBoxRoundFloats + (w * 32 + l);
+    const int flags = (m0 ? 1 : 0) | (m1 ? 2 : 0);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float cf = 0.f, hf = 0.f;
+      if (flags) {
+        const double cd = 0.5 * (lo[c] + hi[c]);
+        cf = (float)cd;
+        // half extent measured from the ROUNDED centre, inflated so the fp32 box contains every point
+        const double hd = fmax(hi[c] - (double)cf, (double)cf - lo[c]);
+        hf = (float)(hd * 1.000001 + (fabs(cd) + hd) * 1.3e-7 + 1e-30);
+      }
+      rec[c * kThreads] = cf;
+      rec[(3 + c) * kThreads] = hf;
+    }
+    rec[6 * kThreads] = __int_as_float(flags);
+    rec[7 * kThreads] = 0.f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Shared-memory layout of one CTA.
 // ------------------------------------------------------------------------------------------
-template <typename CT>
-struct alignas(16) TileBuf {
-  CT x[kTile];
-  CT y[kTile];
-  CT z[kTile];
-  int8_t lab[kTile];
-};
-
-// Self-contained record of a maybe-active point, queued per warp until 32 are pending.
+// Self-contained record of a maybe-active point, queued per warp and label until 64 are pending.
 template <typename CT> struct Entry;
 template <> struct alignas(16) Entry<float> { float x, y, z; int lab; };
 template <> struct alignas(16) Entry<double> { double x, y, z; long long lab; };
-
-__device__ __forceinline__ void load4(const float* p, float o[4]) {
-  const float4 t = *reinterpret_cast<const float4*>(p);
-  o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
-}
-__device__ __forceinline__ void load4(const double* p, double o[4]) {
-  const double2 a = *reinterpret_cast<const double2*>(p);
-  const double2 b = *reinterpret_cast<const double2*>(p + 2);
-  o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
-}
 
 struct LsSample {
   double x, value, gradient;
@@ -348,16 +571,13 @@ struct LMState {
   int ls_iter, evals, ls_steps, term;
 };
 
-constexpr int kSlice = kTile / kWarps;   // points of a tile owned by one warp
-constexpr int kGroup = 128;              // points a warp classifies per step (4 per lane)
-constexpr int kRing = 256;               // pending ring: < 32 carried + at most 128 appended per step
+constexpr int kRing = 128;               // pending ring per label: < 64 carried + at most 32 appended per group
 
 template <typename CT, int P>
 struct Smem {
-  TileBuf<CT> tile[kStages];
-  Entry<CT> list[kWarps][kRing];
-  alignas(8) uint64_t full[kStages];
-  int done[kStages];                     // warps finished with a ring slot
+  alignas(16) float box[kBoxRounds][kBoxRoundFloats];   // bulk-copied (TMA engine) once per problem
+  Entry<CT> list[kWarps][2][kRing];                     // [label 0 | label 1] pending rings
+  alignas(8) uint64_t full;                             // mbarrier of the box-table copy
   double red[kWarps][NAcc<P>::N];
   double tot[NAcc<P>::N];
   PoseConst pose;
@@ -368,112 +588,166 @@ struct Smem {
   int go;            // 1 = another evaluation requested
 };
 
-// ------------------------------------------------------------------------------------------
-// One pass over a cloud: stages tiles, accumulates, block-reduces into sm.tot (all threads must
-// call).  `seq` is the CTA-lifetime count of consumed tiles (selects ring slot and phase).
-// Each warp owns a fixed slice of every tile and runs decoupled from the other warps: fp32
-// culling -> ordered compaction into its pending list -> exact fp64 evaluation of 32 pending
-// points at a time (all lanes busy).  The warp that finishes a ring slot last refills it.
-// ------------------------------------------------------------------------------------------
-template <typename CT>
-__device__ __forceinline__ void issue_tile(TileBuf<CT>* buf, uint64_t* bar, const CT* xyz_s, const int8_t* lab_s,
-                                           int n_stride, int n, int t) {
-  const int base = t * kTile;
-  int cnt = n - base;
-  if (cnt > kTile) cnt = kTile;
-  const int cnt16 = (cnt + 15) & ~15;
-  const uint32_t cb = cnt16 * sizeof(CT);
-  mbar_expect_tx(bar, 3 * cb + cnt16);
-  bulk_g2s(buf->x, xyz_s + base, cb, bar);
-  bulk_g2s(buf->y, xyz_s + n_stride + base, cb, bar);
-  bulk_g2s(buf->z, xyz_s + 2 * (size_t)n_stride + base, cb, bar);
-  bulk_g2s(buf->lab, lab_s + base, cnt16, bar);
+// Box test of one group by one lane: true if the group needs per-point work.
+template <int SMEM>
+__device__ __forceinline__ float box_field(const float* f, int idx) { return SMEM ? f[idx] : __ldg(f + idx); }
+
+template <int SMEM>
+__device__ __forceinline__ bool box_undecided(const float* f, int slot, const ClassConst& cc) {
+  const int flags = __float_as_int(box_field<SMEM>(f, 6 * kThreads + slot));
+  if (flags == 0) return false;                       // no point with a residual block
+  if (!cc.enabled) return true;
+  const float cx = box_field<SMEM>(f, slot), cy = box_field<SMEM>(f, kThreads + slot), cz = box_field<SMEM>(f, 2 * kThreads + slot);
+  const float hx = box_field<SMEM>(f, 3 * kThreads + slot), hy = box_field<SMEM>(f, 4 * kThreads + slot), hz = box_field<SMEM>(f, 5 * kThreads + slot);
+  const float m = 2.0f * fmaf(cc.G, (fabsf(cx) + hx) + (fabsf(cy) + hy) + (fabsf(cz) + hz), cc.G0);
+  float lo[5], hi[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    const float* c = cc.zc + 4 * k;                   // zc, al, ah, bl, bh are contiguous float[4]
+    const float mid = fmaf(c[0], cx, fmaf(c[1], cy, fmaf(c[2], cz, c[3])));
+    const float rad = fmaf(fabsf(c[0]), hx, fmaf(fabsf(c[1]), hy, fabsf(c[2]) * hz));
+    lo[k] = mid - rad; hi[k] = mid + rad;
+  }
+  const bool front = lo[0] > m;
+  const bool all_out = (hi[0] < -m) || (front && (hi[1] < -m || lo[2] > m || hi[3] < -m || lo[4] > m));
+  const bool all_in = front && lo[1] > m && hi[2] < -m && lo[3] > m && hi[4] < -m;
+  const bool skip = (!(flags & 1) || all_out) && (!(flags & 2) || all_in);
+  return !skip;
 }
 
+// ------------------------------------------------------------------------------------------
+// One pass over a cloud (all threads must call): box tests -> coalesced loads of the undecided
+// groups -> per-point fp32 culling -> ordered compaction into the warp's pending rings -> exact
+// fp64 evaluation of 64 pending points at a time (two per lane, label-homogeneous) -> fixed-order
+// block reduction into sm.tot.  Warps never synchronise with each other inside the pass.
+// `boxes_resident` says the sample's whole table already sits in sm.box.
+// ------------------------------------------------------------------------------------------
 template <typename CT, int P>
 __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, int n_stride, int n,
-                               uint32_t& seq) {
+                               const float* box_s, bool boxes_resident, uint32_t& box_phase) {
   constexpr int N = NAcc<P>::N;
-  constexpr int GPT = kSlice / kGroup;   // steps per tile
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int ntiles = (n + kTile - 1) / kTile;
-  if (tid == 0) {
-    const int pre = ntiles < kStages ? ntiles : kStages;
-#pragma unroll 1
-    for (int t = 0; t < pre; ++t) {
-      const uint32_t q = seq + t;
-      issue_tile<CT>(&sm.tile[q % kStages], &sm.full[q % kStages], xyz_s, lab_s, n_stride, n, t);
-    }
-  }
+  const int rounds = box_rounds(n);
   double acc[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) acc[j] = 0.0;
   const Cam& cam = sm.cam;
   const PoseConst& pc = sm.pose;
   const ClassConst& cc = sm.cls;
-  Entry<CT>* ring = sm.list[warp];
-  int head = 0, pending = 0;             // warp-uniform
+  Entry<CT>* ring0 = sm.list[warp][0];
+  Entry<CT>* ring1 = sm.list[warp][1];
+  int head0 = 0, pend0 = 0, head1 = 0, pend1 = 0;   // warp-uniform
+  double prod = 1.0;                                  // per-lane product of (1 + s), renormalised
+  int expo = 0;
 
-  // One flat loop: steps 0 .. ntiles*GPT-1 classify 128 points each and drain full batches of 32;
-  // the extra last step only drains what is left (so the exact evaluation has ONE code instance).
-  const int nsteps = ntiles * GPT;
+  // Rounds r = 0 .. rounds-1 test one box per lane; the extra last round only drains what is left,
+  // so each exact evaluator has ONE code instance.
 #pragma unroll 1
-  for (int step = 0; step <= nsteps; ++step) {
+  for (int r = 0; r <= rounds; ++r) {
+    unsigned mask = 0;
     int threshold = 1;
-    if (step < nsteps) {
-      threshold = 32;
-      const int t = step / GPT, g = step - t * GPT;
-      const uint32_t q = seq + t;
-      const int stage = q % kStages;
-      if (g == 0) mbar_wait(&sm.full[stage], (q / kStages) & 1);
-      const TileBuf<CT>& tb = sm.tile[stage];
-      int tile_cnt = n - t * kTile;
-      if (tile_cnt > kTile) tile_cnt = kTile;
-      const int i0 = warp * kSlice + g * kGroup + lane * 4;
-      CT px[4], py[4], pz[4];
-      load4(tb.x + i0, px);
-      load4(tb.y + i0, py);
-      load4(tb.z + i0, pz);
-      const int lab4 = *reinterpret_cast<const int*>(tb.lab + i0);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int lab = (int)(int8_t)((lab4 >> (8 * j)) & 0xff);
-        const bool mb = (i0 + j < tile_cnt) && maybe_active<P>((float)px[j], (float)py[j], (float)pz[j], lab, cc);
-        const unsigned m = __ballot_sync(0xffffffffu, mb);
-        if (mb) {
-          Entry<CT> e;
-          e.x = px[j]; e.y = py[j]; e.z = pz[j]; e.lab = lab;
-          ring[(head + pending + __popc(m & lt_mask)) & (kRing - 1)] = e;
+    if (r < rounds) {
+      threshold = 64;
+      if (DIB_BOX_SMEM && !boxes_resident && (r % kBoxRounds) == 0) {
+        // clouds larger than the resident window: stream the table chunk by chunk, every pass
+        __syncthreads();
+        if (tid == 0) {
+          int nr = rounds - r;
+          if (nr > kBoxRounds) nr = kBoxRounds;
+          const uint32_t bytes = (uint32_t)nr * kBoxRoundFloats * sizeof(float);
+          mbar_expect_tx(&sm.full, bytes);
+          bulk_g2s(&sm.box[0][0], box_s + (size_t)r * kBoxRoundFloats, bytes, &sm.full);
         }
-        pending += __popc(m);
+        mbar_wait(&sm.full, box_phase & 1);
+        ++box_phase;
       }
-      if (g == GPT - 1) {                // this warp is done with the ring slot
-        __syncwarp();
-        if (lane == 0) {
-          const int old = atomicAdd(&sm.done[stage], 1);
-          if (old == kWarps - 1) {       // last warp out refills it
-            sm.done[stage] = 0;
-            if (t + kStages < ntiles)
-              issue_tile<CT>(&sm.tile[stage], &sm.full[stage], xyz_s, lab_s, n_stride, n, t + kStages);
+#if DIB_BOX_SMEM
+      mask = __ballot_sync(0xffffffffu, box_undecided<1>(sm.box[r % kBoxRounds], warp * 32 + lane, cc));
+#else
+      mask = __ballot_sync(0xffffffffu, box_undecided<0>(box_s + (size_t)r * kBoxRoundFloats, warp * 32 + lane, cc));
+#endif
+    }
+    // Undecided groups are fetched four at a time (all loads in flight before the first use),
+    // then classified one by one; draining happens after each group so the rings cannot overflow.
+    CT gx[4], gy[4], gz[4];
+    int glab[4];
+    int gcount = 0, gnext = 0;
+#pragma unroll 1
+    do {
+      if (gnext == gcount && mask) {
+        gcount = 0; gnext = 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
+          if (mask) {
+            const int b = __ffs(mask) - 1;
+            mask &= mask - 1;
+            ++gcount;
+            const int i = (r * kThreads + b * kWarps + warp) * 32 + lane;      // this lane's point
+            if (i < n) {
+              glab[u] = lab_s[i];
+              gx[u] = xyz_s[i]; gy[u] = xyz_s[n_stride + i]; gz[u] = xyz_s[2 * (size_t)n_stride + i];
+            }
           }
         }
       }
-    }
-#pragma unroll 1
-    while (pending >= threshold) {
-      __syncwarp();
-      const int take = pending < 32 ? pending : 32;
-      if (lane < take) {
-        const Entry<CT> e = ring[(head + lane) & (kRing - 1)];
-        point_accumulate<P>((double)e.x, (double)e.y, (double)e.z, (int)e.lab, cam, pc, acc);
+      if (gnext < gcount) {
+        // select slot gnext without dynamic register indexing
+        CT px = gx[0], py = gy[0], pz = gz[0];
+        int lab = glab[0];
+#pragma unroll
+        for (int u = 1; u < 4; ++u)
+          if (gnext == u) { px = gx[u]; py = gy[u]; pz = gz[u]; lab = glab[u]; }
+        ++gnext;
+        const bool mb = maybe_active<P>((float)px, (float)py, (float)pz, lab, cc);
+        const unsigned m1 = __ballot_sync(0xffffffffu, mb && lab == 1);
+        const unsigned m0 = __ballot_sync(0xffffffffu, mb && lab == 0);
+        if (mb) {
+          Entry<CT> e;
+          e.x = px; e.y = py; e.z = pz; e.lab = lab;
+          if (lab) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
+          else     ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
+        }
+        pend0 += __popc(m0);
+        pend1 += __popc(m1);
       }
-      head = (head + take) & (kRing - 1);
-      pending -= take;
-    }
+#pragma unroll 1
+      while (pend0 >= threshold) {
+        __syncwarp();
+        const int take = pend0 < 64 ? pend0 : 64;
+        const Entry<CT> ea = ring0[(head0 + lane) & (kRing - 1)];
+        const Entry<CT> eb = ring0[(head0 + 32 + lane) & (kRing - 1)];
+        Out0<P> oa, ob;
+        eval_outside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
+        eval_outside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
+        prod *= oa.s1 * ob.s1;
+        renorm_product(prod, expo);
+        rank1<P>(acc, oa.J, oa.w, oa.r);
+        rank1<P>(acc, ob.J, ob.w, ob.r);
+        head0 = (head0 + take) & (kRing - 1);
+        pend0 -= take;
+      }
+#pragma unroll 1
+      while (pend1 >= threshold) {
+        __syncwarp();
+        const int take = pend1 < 64 ? pend1 : 64;
+        const Entry<CT> ea = ring1[(head1 + lane) & (kRing - 1)];
+        const Entry<CT> eb = ring1[(head1 + 32 + lane) & (kRing - 1)];
+        Out1<P> oa, ob;
+        eval_inside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
+        eval_inside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
+        prod *= oa.s1 * ob.s1;
+        renorm_product(prod, expo);
+        accumulate_inside<P>(acc, oa);
+        accumulate_inside<P>(acc, ob);
+        head1 = (head1 + take) & (kRing - 1);
+        pend1 -= take;
+      }
+    } while (mask || gnext < gcount);
   }
-  seq += ntiles;
+  acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
   // fixed-order reduction: butterfly inside the warp, then warps 0..kWarps-1 in order
 #pragma unroll
@@ -497,14 +771,33 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
   __syncthreads();
 }
 
+// Loads a sample's whole box table into shared memory if it fits the resident window (all
+// threads call; returns true if resident).
+template <typename CT, int P>
+__device__ bool load_boxes(Smem<CT, P>& sm, const float* box_s, int n, uint32_t& box_phase) {
+  const int rounds = box_rounds(n);
+  if (!DIB_BOX_SMEM) return true;
+  if (rounds > kBoxRounds) return false;
+  if (rounds > 0) {
+    if (threadIdx.x == 0) {
+      const uint32_t bytes = (uint32_t)rounds * kBoxRoundFloats * sizeof(float);
+      mbar_expect_tx(&sm.full, bytes);
+      bulk_g2s(&sm.box[0][0], box_s, bytes, &sm.full);
+    }
+    mbar_wait(&sm.full, box_phase & 1);
+    ++box_phase;
+  }
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Trust-region control flow (thread 0 only).
 // ------------------------------------------------------------------------------------------
 template <int P>
-__device__ __noinline__ void project_plus(const LMState<P>& st, const double* x, const double* d, double a, double* out) {
-  #pragma unroll 1
+__device__ __forceinline__ void project_plus(const LMState<P>& st, const double* x, const double* d, double a, double* out) {
+#pragma unroll
   for (int j = 0; j < P; ++j) {
-    double v = x[j] + a * d[j];
+    double v = fma(a, d[j], x[j]);
     v = fmax(v, st.lb[j]);
     v = fmin(v, st.ub[j]);
     out[j] = v;
@@ -512,9 +805,9 @@ __device__ __noinline__ void project_plus(const LMState<P>& st, const double* x,
 }
 
 template <int P>
-__device__ __noinline__ double grad_max_norm(const LMState<P>& st, const double* x, const double* g) {
+__device__ __forceinline__ double grad_max_norm(const LMState<P>& st, const double* x, const double* g) {
   double mx = 0.0;
-  #pragma unroll 1
+#pragma unroll
   for (int j = 0; j < P; ++j) {
     double v = x[j] - g[j];
     v = fmax(v, st.lb[j]);
@@ -524,41 +817,44 @@ __device__ __noinline__ double grad_max_norm(const LMState<P>& st, const double*
   return mx;
 }
 
-// Solve (As + diag(d2)) y = gs by Cholesky; As given as packed upper triangle.  false if not SPD.
+// Solve (As + diag(d2)) y = gs by Cholesky, As full symmetric P x P in registers.  One rsqrt per
+// column and no divisions (the control code is latency-bound on one thread).  false if not SPD.
 template <int P>
-__device__ __noinline__ bool chol_solve(const double* As, const double* d2, const double* gs, double* y) {
-  double L[P][P];
-  #pragma unroll 1
+__device__ __forceinline__ bool chol_solve(const double (&As)[P][P], const double* d2, const double* gs, double* y) {
+  double L[P][P], inv[P];
+  bool ok = true;
+#pragma unroll
   for (int j = 0; j < P; ++j) {
-    #pragma unroll 1
-    for (int i = j; i < P; ++i) {
-      double s = As[tri(P, j, i)] + (i == j ? d2[j] : 0.0);
-      #pragma unroll 1
-      for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
-      if (i == j) {
-        if (!(s > 0.0)) return false;
-        L[j][j] = sqrt(s);
-      } else {
-        L[i][j] = s / L[j][j];
-      }
+    double s = As[j][j] + d2[j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) s = fma(-L[j][k], L[j][k], s);
+    if (!(s > 0.0)) ok = false;
+    inv[j] = rsqrt(s);
+    L[j][j] = s * inv[j];
+#pragma unroll
+    for (int i = j + 1; i < P; ++i) {
+      double t = As[i][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t = fma(-L[i][k], L[j][k], t);
+      L[i][j] = t * inv[j];
     }
   }
   double z[P];
-  #pragma unroll 1
+#pragma unroll
   for (int i = 0; i < P; ++i) {
-    double s = gs[i];
-    #pragma unroll 1
-    for (int k = 0; k < i; ++k) s -= L[i][k] * z[k];
-    z[i] = s / L[i][i];
+    double t = gs[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) t = fma(-L[i][k], z[k], t);
+    z[i] = t * inv[i];
   }
-  #pragma unroll 1
+#pragma unroll
   for (int i = P - 1; i >= 0; --i) {
-    double s = z[i];
-    #pragma unroll 1
-    for (int k = i + 1; k < P; ++k) s -= L[k][i] * y[k];
-    y[i] = s / L[i][i];
+    double t = z[i];
+#pragma unroll
+    for (int k = i + 1; k < P; ++k) t = fma(-L[k][i], y[k], t);
+    y[i] = t * inv[i];
   }
-  return true;
+  return ok;
 }
 
 __device__ double poly_eval(const double* p, int n, double x) {   // n coefficients, highest first
@@ -729,7 +1025,6 @@ enum { LM_DONE = 0, LM_EVAL = 1 };
 // Starts the next trust-region iteration(s) until an evaluation is needed or the solve ends.
 template <int P>
 __device__ __noinline__ int lm_next_step(LMState<P>& st) {
-  constexpr int NA = NAcc<P>::NA;
   for (;;) {
     if (st.iteration >= st.max_iter) { st.term = 3; return LM_DONE; }
     if (st.step_ok && st.grad_max <= 1e-10) { st.term = 0; return LM_DONE; }
@@ -737,36 +1032,46 @@ __device__ __noinline__ int lm_next_step(LMState<P>& st) {
     ++st.iteration;
     st.step_ok = 0;
 
-    double As[NA], gs[P], d2[P], y[P];
-    #pragma unroll 1
-    for (int j = 0; j < P; ++j) {
-      gs[j] = st.g[j] * st.scale[j];
-      #pragma unroll 1
-      for (int k = j; k < P; ++k) As[tri(P, j, k)] = st.A[tri(P, j, k)] * st.scale[j] * st.scale[k];
+    double As[P][P], gs[P], d2[P], y[P], sc[P];
+#pragma unroll
+    for (int j = 0; j < P; ++j) { sc[j] = st.scale[j]; gs[j] = st.g[j] * sc[j]; }
+    {
+      int idx = 0;
+#pragma unroll
+      for (int j = 0; j < P; ++j)
+#pragma unroll
+        for (int k = j; k < P; ++k) {
+          const double v = st.A[idx++] * sc[j] * sc[k];
+          As[j][k] = v; As[k][j] = v;
+        }
     }
-    if (!st.reuse_diag)
-      #pragma unroll 1
-      for (int j = 0; j < P; ++j) st.diag[j] = fmin(fmax(As[tri(P, j, j)], 1e-6), 1e32);
+    if (!st.reuse_diag) {
+#pragma unroll
+      for (int j = 0; j < P; ++j) st.diag[j] = fmin(fmax(As[j][j], 1e-6), 1e32);
+    }
     st.reuse_diag = 1;
-    #pragma unroll 1
-    for (int j = 0; j < P; ++j) { const double l = sqrt(st.diag[j] / st.radius); d2[j] = l * l; }
+    {
+      const double inv_radius = 1.0 / st.radius;      // D^2 = diag / radius (LM damping)
+#pragma unroll
+      for (int j = 0; j < P; ++j) d2[j] = st.diag[j] * inv_radius;
+    }
     bool ok = chol_solve<P>(As, d2, gs, y);
     double mcc = 0.0;
     if (ok) {
       // model cost change = -step^T gs - 1/2 step^T As step, step = -y
       double quad = 0.0, lin = 0.0;
-      #pragma unroll 1
+#pragma unroll
       for (int j = 0; j < P; ++j) {
         st.step[j] = -y[j];
-        if (!isfinite(st.step[j])) ok = false;
+        if (!isfinite(y[j])) ok = false;
       }
-      #pragma unroll 1
+#pragma unroll
       for (int j = 0; j < P; ++j) {
-        lin += st.step[j] * gs[j];
+        lin = fma(-y[j], gs[j], lin);
         double rowsum = 0.0;
-        #pragma unroll 1
-        for (int k = 0; k < P; ++k) rowsum += As[j <= k ? tri(P, j, k) : tri(P, k, j)] * st.step[k];
-        quad += st.step[j] * rowsum;
+#pragma unroll
+        for (int k = 0; k < P; ++k) rowsum = fma(As[j][k], -y[k], rowsum);
+        quad = fma(-y[j], rowsum, quad);
       }
       mcc = -lin - 0.5 * quad;
     }
@@ -779,7 +1084,7 @@ __device__ __noinline__ int lm_next_step(LMState<P>& st) {
     st.invalid = 0;
     st.mcc = mcc;
     double gd = 0.0, dmax = 0.0;
-    #pragma unroll 1
+#pragma unroll
     for (int j = 0; j < P; ++j) {
       st.delta[j] = st.step[j] * st.scale[j];
       gd += st.g[j] * st.delta[j];
@@ -801,18 +1106,18 @@ __device__ __noinline__ int lm_after_candidate(LMState<P>& st, const double* tot
   constexpr int NA = NAcc<P>::NA;
   const double ccost = tot[0];
   double sn = 0.0;
-  #pragma unroll 1
+#pragma unroll
   for (int j = 0; j < P; ++j) sn += (st.x[j] - st.xt[j]) * (st.x[j] - st.xt[j]);
   if (sqrt(sn) <= 1e-8 * (st.x_norm + 1e-8)) { st.term = 1; return LM_DONE; }
   if (fabs(st.cost - ccost) <= 1e-6 * st.cost) { st.term = 2; return LM_DONE; }
   const double rho = (st.cost - ccost) / st.mcc;
   if (rho > 1e-3) {
     double xn = 0.0;
-    #pragma unroll 1
+#pragma unroll
     for (int j = 0; j < P; ++j) { st.x[j] = st.xt[j]; xn += st.x[j] * st.x[j]; st.g[j] = tot[1 + j]; }
     st.x_norm = sqrt(xn);
     st.cost = ccost;
-    #pragma unroll 1
+#pragma unroll
     for (int j = 0; j < NA; ++j) st.A[j] = tot[1 + P + j];
     st.grad_max = grad_max_norm<P>(st, st.x, st.g);
     const double t = 2.0 * rho - 1.0;
@@ -933,19 +1238,21 @@ struct SolveArgs {
   double* cost_all;     // [S*I]
   int32_t* stats_all;   // [S*I*4]
   unsigned int* queue;  // problem counter
+  const float* boxes;   // [S][rounds_max][8][kThreads] box table
+  int rounds_max;
 };
 
 template <typename CT, int P>
-__global__ void __launch_bounds__(kThreads, (P == 4) ? 4 : 3) frustum_solve_kernel(SolveArgs a) {
+__global__ void __launch_bounds__(kThreads, (P == 4) ? DIB_MINBLOCKS4 : DIB_MINBLOCKS6) frustum_solve_kernel(SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
   const int tid = threadIdx.x;
   if (tid == 0) {
-    for (int s = 0; s < kStages; ++s) { mbar_init(&sm.full[s], 1); sm.done[s] = 0; }
+    mbar_init(&sm.full, 1);
     mbar_fence_init();
   }
   __syncthreads();
-  uint32_t seq = 0;
+  uint32_t box_phase = 0;
   const int total = a.S * a.I;
 
   for (;;) {
@@ -956,6 +1263,7 @@ __global__ void __launch_bounds__(kThreads, (P == 4) ? 4 : 3) frustum_solve_kern
     const int s = prob / a.I;
     const CT* xyz_s = reinterpret_cast<const CT*>(a.xyz) + (size_t)s * 3 * a.n_stride;
     const int8_t* lab_s = a.label + (size_t)s * a.n_stride;
+    const float* box_s = a.boxes + (size_t)s * a.rounds_max * kBoxRoundFloats;
     const int n = a.n_pts ? a.n_pts[s] : a.n_stride;
     if (tid == 0) {
       make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &sm.cam);
@@ -963,9 +1271,10 @@ __global__ void __launch_bounds__(kThreads, (P == 4) ? 4 : 3) frustum_solve_kern
       sm.go = rc;
       if (rc == LM_EVAL) { make_pose<P>(sm.lm.xt, &sm.pose); make_class(sm.pose, sm.cam, &sm.cls); }
     }
+    const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);   // overlaps thread 0's set-up
     __syncthreads();
     while (sm.go == LM_EVAL) {
-      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, a.n_stride, n, seq);
+      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, a.n_stride, n, box_s, resident, box_phase);
       if (tid == 0) {
         const int rc = lm_consume<P>(sm.lm, sm.tot);
         sm.go = rc;
@@ -1031,23 +1340,28 @@ template <typename CT, int P>
 __global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xyz, const int8_t* label,
                                                                      const int32_t* n_pts, int n_stride,
                                                                      const double* K9, const double* x, double H,
-                                                                     double W, double* cost_out, double* grad_out,
+                                                                     double W, const float* boxes, int rounds_max,
+                                                                     double* cost_out, double* grad_out,
                                                                      double* JtJ_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
   const int tid = threadIdx.x;
   const int s = blockIdx.x;
   if (tid == 0) {
-    for (int k = 0; k < kStages; ++k) { mbar_init(&sm.full[k], 1); sm.done[k] = 0; }
+    mbar_init(&sm.full, 1);
     mbar_fence_init();
     make_cam(K9 + (size_t)s * 9, H, W, &sm.cam);
     make_pose<P>(x + (size_t)s * 6, &sm.pose);
     make_class(sm.pose, sm.cam, &sm.cls);
   }
   __syncthreads();
-  uint32_t seq = 0;
+  uint32_t box_phase = 0;
   const int n = n_pts ? n_pts[s] : n_stride;
-  evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride, n_stride, n, seq);
+  const float* box_s = boxes + (size_t)s * rounds_max * kBoxRoundFloats;
+  const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);
+  __syncthreads();
+  evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride, n_stride, n, box_s, resident,
+                        box_phase);
   if (tid == 0) {
     cost_out[s] = sm.tot[0];
     for (int j = 0; j < 6; ++j) grad_out[(size_t)s * 6 + j] = (j < P) ? sm.tot[1 + j] : 0.0;
@@ -1085,6 +1399,22 @@ __global__ void frustum_residuals_kernel(const CT* xyz, const int8_t* label, int
 // Host side of the C ABI.
 // ------------------------------------------------------------------------------------------
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+static size_t box_table_bytes(int S, int n_stride) {
+  return align_up((size_t)(S > 0 ? S : 0) * box_rounds(n_stride) * kBoxRoundFloats * sizeof(float), 256);
+}
+
+template <typename CT>
+static int launch_boxes(const CT* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, int S, float* table,
+                        cudaStream_t st) {
+  const int rounds_max = box_rounds(n_stride);
+  if (rounds_max == 0 || S == 0) return DIB_OK;
+  DIB_REQUIRE(S <= 65535, "S (%d) exceeds grid.y; split the batch", S);
+  const int groups = rounds_max * kThreads;
+  dim3 grid((groups + 7) / 8, S);
+  frustum_boxes_kernel<CT><<<grid, 256, 0, st>>>(xyz, label, n_pts, n_stride, rounds_max, table);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
 
 template <typename CT>
 static int check_cloud_args(const CT* xyz, const int8_t* label, int n_stride, int S) {
@@ -1126,8 +1456,8 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   DIB_REQUIRE(K9 && init && lb3 && ub3 && P16_out && cost_out, "NULL argument");
   DIB_REQUIRE((long long)S * I < (1ll << 31), "S*I too large");
   if (S == 0) return DIB_OK;
-  if (workspace_bytes < frustum_solve_workspace_bytes(S, I) || workspace == nullptr) {
-    set_error("workspace too small: %zu < %zu", workspace_bytes, frustum_solve_workspace_bytes(S, I));
+  if (workspace_bytes < frustum_solve_workspace_bytes(S, I, n_stride) || workspace == nullptr) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, frustum_solve_workspace_bytes(S, I, n_stride));
     return DIB_ENOMEM;
   }
   cudaStream_t st = (cudaStream_t)stream;
@@ -1141,10 +1471,16 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   a.cost_all = cost_all ? cost_all : (double*)(ws + off);
   off += align_up(n * sizeof(double), 256);
   a.stats_all = stats_all ? stats_all : (int32_t*)(ws + off);
+  off += align_up(n * 4 * sizeof(int32_t), 256);
+  float* table = (float*)(ws + off);
+  a.boxes = table;
+  a.rounds_max = box_rounds(n_stride);
   a.xyz = xyz; a.label = label; a.n_pts = n_pts; a.n_stride = n_stride; a.K9 = K9; a.init = init;
   for (int k = 0; k < 3; ++k) { a.lb[k] = lb3[k]; a.ub[k] = ub3[k]; }
   a.H = H; a.W = W; a.max_iter = max_iter; a.S = S; a.I = I;
   DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
+  rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, st);
+  if (rc != DIB_OK) return rc;
   rc = is_2d ? launch_solve<CT, 4>(a, st) : launch_solve<CT, 6>(a, st);
   if (rc != DIB_OK) return rc;
   frustum_finalize_kernel<<<(S + 127) / 128, 128, 0, st>>>(a.params_all, a.cost_all, S, I, is_2d ? 4 : 6, P16_out,
@@ -1156,22 +1492,32 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
 template <typename CT>
 static int evaluate_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
                           const double* x, double H, double W, int is_2d, int S, double* cost_out, double* grad_out,
-                          double* JtJ_out, dib_stream_t stream) {
+                          double* JtJ_out, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
   int rc = check_cloud_args<CT>(xyz, label, n_stride, S);
   if (rc != DIB_OK) return rc;
   DIB_REQUIRE(K9 && x && cost_out && grad_out && JtJ_out, "NULL argument");
   if (S == 0) return DIB_OK;
+  if (workspace_bytes < frustum_evaluate_workspace_bytes(S, n_stride) || workspace == nullptr) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, frustum_evaluate_workspace_bytes(S, n_stride));
+    return DIB_ENOMEM;
+  }
   cudaStream_t st = (cudaStream_t)stream;
+  float* table = (float*)workspace;
+  const int rounds_max = box_rounds(n_stride);
+  rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, st);
+  if (rc != DIB_OK) return rc;
   if (is_2d) {
     auto kern = frustum_evaluate_kernel<CT, 4>;
     const size_t smem = sizeof(Smem<CT, 4>);
     DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, cost_out, grad_out, JtJ_out);
+    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, rounds_max, cost_out, grad_out,
+                                    JtJ_out);
   } else {
     auto kern = frustum_evaluate_kernel<CT, 6>;
     const size_t smem = sizeof(Smem<CT, 6>);
     DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, cost_out, grad_out, JtJ_out);
+    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, rounds_max, cost_out, grad_out,
+                                    JtJ_out);
   }
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
@@ -1198,7 +1544,7 @@ static int residuals_single(const CT* xyz, const int8_t* label, int n, int n_str
 
 extern "C" {
 
-int dib_abi_version(void) { return 1; }
+int dib_abi_version(void) { return 2; }
 const char* dib_last_error(void) { return dib::g_err; }
 
 int dib_device_sm_count(void) {
@@ -1208,10 +1554,14 @@ int dib_device_sm_count(void) {
   return sms;
 }
 
-size_t frustum_solve_workspace_bytes(int S, int I) {
+size_t frustum_solve_workspace_bytes(int S, int I, int n_stride) {
   const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
   return 256 + dib::align_up(n * 6 * sizeof(double), 256) + dib::align_up(n * sizeof(double), 256) +
-         dib::align_up(n * 4 * sizeof(int32_t), 256);
+         dib::align_up(n * 4 * sizeof(int32_t), 256) + dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0);
+}
+
+size_t frustum_evaluate_workspace_bytes(int S, int n_stride) {
+  return dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0) + 256;
 }
 
 int frustum_solve_batch_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
@@ -1236,15 +1586,16 @@ int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_
 
 int frustum_evaluate_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
                          const double* x, double H, double W, int is_2d, int S, double* cost_out, double* grad_out,
-                         double* JtJ_out, dib_stream_t stream) {
+                         double* JtJ_out, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
   return dib::evaluate_batch<float>(xyz, label, n_pts, n_stride, K9, x, H, W, is_2d, S, cost_out, grad_out, JtJ_out,
-                                    stream);
+                                    workspace, workspace_bytes, stream);
 }
 int frustum_evaluate_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
                          const double* K9, const double* x, double H, double W, int is_2d, int S, double* cost_out,
-                         double* grad_out, double* JtJ_out, dib_stream_t stream) {
+                         double* grad_out, double* JtJ_out, void* workspace, size_t workspace_bytes,
+                         dib_stream_t stream) {
   return dib::evaluate_batch<double>(xyz, label, n_pts, n_stride, K9, x, H, W, is_2d, S, cost_out, grad_out, JtJ_out,
-                                     stream);
+                                     workspace, workspace_bytes, stream);
 }
 
 int frustum_residuals_f32(const float* xyz, const int8_t* label, int n, int n_stride, const double* K9,

@@ -16,8 +16,9 @@
 
 namespace dib {
 
-constexpr int kPrepThreads = 256;
+constexpr int kPrepThreads = 1024;
 constexpr int kPrepWarps = kPrepThreads / 32;
+constexpr int kSortMax = 32768;          // points sortable in shared memory (32-bit composite keys)
 constexpr double kPi = 3.14159265358979323846;
 
 __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -31,36 +32,40 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
   }
 }
 
-__device__ double block_sum(double v, double* scratch) {
+template <typename T, typename Op>
+__device__ T block_reduce(T v, T* scratch, Op op) {
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  for (int o = 16; o > 0; o >>= 1) v = op(v, __shfl_xor_sync(0xffffffffu, v, o));
   __syncthreads();
   if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
   __syncthreads();
-  double t = scratch[0];
-  for (int w = 1; w < kPrepWarps; ++w) t += scratch[w];
+  T t = scratch[0];
+  for (int w = 1; w < kPrepWarps; ++w) t = op(t, scratch[w]);   // fixed order
   return t;
 }
 
-__device__ double block_min(double v, double* scratch) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-  __syncthreads();
-  double t = scratch[0];
-  for (int w = 1; w < kPrepWarps; ++w) t = fmin(t, scratch[w]);
-  return t;
+__device__ __forceinline__ uint32_t spread6(uint32_t v) {   // 6 bits -> every other bit
+  v &= 0x3f;
+  v = (v | (v << 4)) & 0x30f;
+  v = (v | (v << 2)) & 0x333;
+  v = (v | (v << 1)) & 0x555;
+  return v;
 }
 
 // grid = S.  xyz_in [S][3][n_in_stride] f32, pred [S][n_in_stride] int8, n_in points valid.
+// do_sort: order the kept points by (label class, 12-bit Morton cell of (x, z), original index) with an
+// in-shared-memory bitonic sort of 32-bit composite keys (needs n_in <= kSortMax and n2 * 4 bytes of
+// dynamic shared memory, n2 = next power of two >= n_in); otherwise the original order is kept.
 __global__ void __launch_bounds__(kPrepThreads)
     frustum_prepare_kernel(const float* __restrict__ xyz_in, const int8_t* __restrict__ pred, int n_in,
                            int n_in_stride, int n_out_stride, int I, unsigned long long seed, double ry_sigma,
-                           double t_amp, float* __restrict__ xyz_out, int8_t* __restrict__ label_out,
-                           int32_t* __restrict__ n_pts, double* __restrict__ init, double* __restrict__ init_y_angle,
-                           int32_t* __restrict__ degenerate) {
+                           double t_amp, int do_sort, int n2, float* __restrict__ xyz_out,
+                           int8_t* __restrict__ label_out, int32_t* __restrict__ n_pts, double* __restrict__ init,
+                           double* __restrict__ init_y_angle, int32_t* __restrict__ degenerate) {
+  extern __shared__ __align__(16) uint32_t keys[];
   __shared__ double scratch[kPrepWarps];
+  __shared__ float fscratch[kPrepWarps];
+  __shared__ int iscratch[kPrepWarps];
   __shared__ int warp_cnt[kPrepWarps];
   __shared__ int s_base;
   const int s = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -68,13 +73,14 @@ __global__ void __launch_bounds__(kPrepThreads)
   const float* py = px + n_in_stride;
   const float* pz = py + n_in_stride;
   const int8_t* lab = pred + (size_t)s * n_in_stride;
+  auto dsum = [](double a, double b) { return a + b; };
+  auto dmin = [](double a, double b) { return fmin(a, b); };
 
   // pass 1: mean of predicted-inside points (fixed reduction order)
-  double sx = 0, sy = 0, sz = 0, cnt = 0;
+  double sx = 0, sz = 0, cnt = 0;
   for (int i = tid; i < n_in; i += kPrepThreads)
-    if (lab[i] == 1) { sx += (double)px[i]; sy += (double)py[i]; sz += (double)pz[i]; cnt += 1.0; }
-  sx = block_sum(sx, scratch); sz = block_sum(sz, scratch); cnt = block_sum(cnt, scratch);
-  (void)sy;
+    if (lab[i] == 1) { sx += (double)px[i]; sz += (double)pz[i]; cnt += 1.0; }
+  sx = block_reduce(sx, scratch, dsum); sz = block_reduce(sz, scratch, dsum); cnt = block_reduce(cnt, scratch, dsum);
   const bool degen = !(cnt > 0.0);
   double ang = 0.0;
   if (!degen) {
@@ -90,39 +96,97 @@ __global__ void __launch_bounds__(kPrepThreads)
   double zmin = DBL_MAX;
   for (int i = tid; i < n_in; i += kPrepThreads)
     if (lab[i] == 1) zmin = fmin(zmin, -sn * (double)px[i] + cs * (double)pz[i]);
-  zmin = block_min(zmin, scratch);
+  zmin = block_reduce(zmin, scratch, dmin);
   const double thresh = zmin - 10.0;
 
-  // pass 3: order-preserving compaction of the front points (:213-215)
   float* ox = xyz_out + (size_t)s * 3 * n_out_stride;
   float* oy = ox + n_out_stride;
   float* oz = oy + n_out_stride;
   int8_t* ol = label_out + (size_t)s * n_out_stride;
-  if (tid == 0) s_base = 0;
-  __syncthreads();
-  for (int start = 0; start < n_in; start += kPrepThreads) {
-    const int i = start + tid;
-    bool keep = false;
-    float x = 0, y = 0, z = 0;
-    int8_t l = -1;
-    if (i < n_in) {
-      x = px[i]; y = py[i]; z = pz[i]; l = lab[i];
-      keep = degen ? true : ((-sn * (double)x + cs * (double)z) > thresh);
+  int n_front;
+
+  if (do_sort) {
+    // pass 3a: extent of the kept points in (x, z) for the Morton quantisation
+    float xlo = 3e38f, xhi = -3e38f, zlo = 3e38f, zhi = -3e38f;
+    int kept = 0;
+    for (int i = tid; i < n_in; i += kPrepThreads) {
+      const float x = px[i], z = pz[i];
+      if (degen || (-sn * (double)x + cs * (double)z) > thresh) {
+        ++kept;
+        xlo = fminf(xlo, x); xhi = fmaxf(xhi, x); zlo = fminf(zlo, z); zhi = fmaxf(zhi, z);
+      }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, keep);
-    if (lane == 0) warp_cnt[warp] = __popc(m);
-    __syncthreads();
-    int off = s_base;
-    for (int w = 0; w < warp; ++w) off += warp_cnt[w];
-    if (keep) {
-      const int o = off + __popc(m & ((1u << lane) - 1u));
-      if (o < n_out_stride) { ox[o] = x; oy[o] = y; oz[o] = z; ol[o] = (l == 0 || l == 1) ? l : (int8_t)-1; }
+    auto fmn = [](float a, float b) { return fminf(a, b); };
+    auto fmx = [](float a, float b) { return fmaxf(a, b); };
+    auto isum = [](int a, int b) { return a + b; };
+    xlo = block_reduce(xlo, fscratch, fmn); xhi = block_reduce(xhi, fscratch, fmx);
+    zlo = block_reduce(zlo, fscratch, fmn); zhi = block_reduce(zhi, fscratch, fmx);
+    n_front = block_reduce(kept, iscratch, isum);
+    const float xs = (xhi > xlo) ? 64.0f / (xhi - xlo) : 0.0f, zs = (zhi > zlo) ? 64.0f / (zhi - zlo) : 0.0f;
+    // pass 3b: composite keys  [class:2 | morton:12 | index:15], dropped points and padding sort last
+    for (int i = tid; i < n2; i += kPrepThreads) {
+      uint32_t key = 0xFFFFFFFFu;
+      if (i < n_in) {
+        const float x = px[i], z = pz[i];
+        if (degen || (-sn * (double)x + cs * (double)z) > thresh) {
+          const int l = lab[i];
+          const uint32_t cls = (l == 0) ? 0u : (l == 1 ? 1u : 2u);
+          const uint32_t qx = (uint32_t)fminf(fmaxf((x - xlo) * xs, 0.0f), 63.0f);
+          const uint32_t qz = (uint32_t)fminf(fmaxf((z - zlo) * zs, 0.0f), 63.0f);
+          key = (cls << 27) | (((spread6(qx) << 1) | spread6(qz)) << 15) | (uint32_t)i;
+        }
+      }
+      keys[i] = key;
     }
     __syncthreads();
-    if (tid == 0) { int t = 0; for (int w = 0; w < kPrepWarps; ++w) t += warp_cnt[w]; s_base += t; }
+    // pass 3c: bitonic sort (keys are unique -> deterministic)
+    for (int k = 2; k <= n2; k <<= 1) {
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < (n2 >> 1); t += kPrepThreads) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const uint32_t a = keys[i], b = keys[i | j];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { keys[i] = b; keys[i | j] = a; }
+        }
+        __syncthreads();
+      }
+    }
+    // pass 3d: gather in sorted order
+    if (n_front > n_out_stride) n_front = n_out_stride;
+    for (int i = tid; i < n_front; i += kPrepThreads) {
+      const int src = (int)(keys[i] & 0x7FFFu);
+      const int8_t l = lab[src];
+      ox[i] = px[src]; oy[i] = py[src]; oz[i] = pz[src];
+      ol[i] = (l == 0 || l == 1) ? l : (int8_t)-1;
+    }
+  } else {
+    // pass 3: order-preserving compaction of the front points (:213-215)
+    if (tid == 0) s_base = 0;
     __syncthreads();
+    for (int start = 0; start < n_in; start += kPrepThreads) {
+      const int i = start + tid;
+      bool keep = false;
+      float x = 0, y = 0, z = 0;
+      int8_t l = -1;
+      if (i < n_in) {
+        x = px[i]; y = py[i]; z = pz[i]; l = lab[i];
+        keep = degen ? true : ((-sn * (double)x + cs * (double)z) > thresh);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) warp_cnt[warp] = __popc(m);
+      __syncthreads();
+      int off = s_base;
+      for (int w = 0; w < warp; ++w) off += warp_cnt[w];
+      if (keep) {
+        const int o = off + __popc(m & ((1u << lane) - 1u));
+        if (o < n_out_stride) { ox[o] = x; oy[o] = y; oz[o] = z; ol[o] = (l == 0 || l == 1) ? l : (int8_t)-1; }
+      }
+      __syncthreads();
+      if (tid == 0) { int t = 0; for (int w = 0; w < kPrepWarps; ++w) t += warp_cnt[w]; s_base += t; }
+      __syncthreads();
+    }
+    n_front = min(s_base, n_out_stride);
   }
-  const int n_front = min(s_base, n_out_stride);
   for (int i = n_front + tid; i < n_out_stride; i += kPrepThreads) { ox[i] = 0.f; oy[i] = 0.f; oz[i] = 0.f; ol[i] = -1; }
   if (tid == 0) {
     n_pts[s] = n_front;
@@ -157,9 +221,10 @@ size_t frustum_prepare_workspace_bytes(int S, int I) {
 // xyz_in [S][3][n_in_stride] f32 [dev], pred [S][n_in_stride] int8 [dev] (1 = predicted inside);
 // outputs: xyz_out [S][3][n_out_stride], label_out [S][n_out_stride], n_pts [S], init [S][I][4],
 // init_y_angle [S], degenerate [S] (1 = no predicted-inside point; registration_lsq.py:329-332).
-// n_out_stride must be a multiple of 16 and >= n_in.
+// n_out_stride = round_up(n_in, 16).  sort != 0 reorders the kept points by (label, Morton cell) -- the
+// solver's sums are order-independent up to rounding and its box culling is far more effective on it.
 int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in, int n_in_stride, int S, int I,
-                              uint64_t seed, double ry_sigma, double t_amp, float* xyz_out, int8_t* label_out,
+                              uint64_t seed, double ry_sigma, double t_amp, int sort, float* xyz_out, int8_t* label_out,
                               int32_t* n_pts, double* init, double* init_y_angle, int32_t* degenerate,
                               void* workspace, size_t workspace_bytes, dib_stream_t stream) {
   using namespace dib;
@@ -168,9 +233,15 @@ int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in,
   DIB_REQUIRE(S >= 0 && I >= 1 && n_in >= 0 && n_in <= n_in_stride, "bad sizes");
   const int n_out_stride = (n_in + 15) & ~15;
   if (S == 0) return DIB_OK;
-  frustum_prepare_kernel<<<S, kPrepThreads, 0, (cudaStream_t)stream>>>(xyz_in, pred, n_in, n_in_stride, n_out_stride,
-                                                                        I, seed, ry_sigma, t_amp, xyz_out, label_out,
-                                                                        n_pts, init, init_y_angle, degenerate);
+  const int do_sort = (sort != 0 && n_in <= kSortMax && n_in > 1) ? 1 : 0;
+  int n2 = 1;
+  while (n2 < n_in) n2 <<= 1;
+  const size_t smem = do_sort ? (size_t)n2 * sizeof(uint32_t) : 0;
+  if (smem > 48 * 1024)
+    DIB_CHECK_CUDA(cudaFuncSetAttribute(frustum_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  frustum_prepare_kernel<<<S, kPrepThreads, smem, (cudaStream_t)stream>>>(
+      xyz_in, pred, n_in, n_in_stride, n_out_stride, I, seed, ry_sigma, t_amp, do_sort, n2, xyz_out, label_out, n_pts,
+      init, init_y_angle, degenerate);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }

@@ -134,7 +134,7 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
             params = torch.empty((S, I, 6), dtype=torch.float64, device=dev)
             costs = torch.empty((S, I), dtype=torch.float64, device=dev)
             stats = torch.empty((S, I, 4), dtype=torch.int32, device=dev)
-        wsb = lib.frustum_solve_workspace_bytes(S, I)
+        wsb = lib.frustum_solve_workspace_bytes(S, I, Ns)
         ws = _workspace(wsb, dev)
         fn = lib.frustum_solve_batch_f32 if xyz.dtype == torch.float32 else lib.frustum_solve_batch_f64
         rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(init), lb.ctypes.data, ub.ctypes.data,
@@ -159,9 +159,10 @@ def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None):
         cost = torch.empty((S,), dtype=torch.float64, device=dev)
         grad = torch.empty((S, 6), dtype=torch.float64, device=dev)
         JtJ = torch.empty((S, 36), dtype=torch.float64, device=dev)
+        ws = _workspace(lib.frustum_evaluate_workspace_bytes(S, Ns), dev)
         fn = lib.frustum_evaluate_f32 if xyz.dtype == torch.float32 else lib.frustum_evaluate_f64
         rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(x), float(H), float(W), 1 if is_2d else 0, S,
-                _ptr(cost), _ptr(grad), _ptr(JtJ), _stream_ptr(stream))
+                _ptr(cost), _ptr(grad), _ptr(JtJ), _ptr(ws), ws.numel(), _stream_ptr(stream))
     _native.check(rc, "frustum_evaluate")
     P = 4 if is_2d else 6
     return cost, grad[:, :P], JtJ[:, :P * P].reshape(S, P, P)
@@ -190,11 +191,13 @@ def residuals(xyz, label, n, K, x, H, W, is_2d=True, stream=None):
     return res[:total]
 
 
-def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=T_AMPLITUDE, stream=None):
+def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=T_AMPLITUDE, sort=True,
+                  stream=None):
     """On-device get_initial_guess + init perturbation (registration_lsq.py:196-220, 163-164).
 
-    xyz_in [S,3,Ns_in] f32 cuda, pred [S,Ns_in] int8 cuda.  Returns dict(xyz, label, n_pts, init,
-    init_y_angle, degenerate) ready for solve_batch."""
+    xyz_in [S,3,Ns_in] f32 cuda, pred [S,Ns_in] int8 cuda.  sort=True additionally orders the kept
+    points by (label, Morton cell) so that the solver's box culling bites.  Returns dict(xyz, label,
+    n_pts, init, init_y_angle, degenerate) ready for solve_batch."""
     _require_cuda()
     lib = _native.load()
     S, _, Ns_in = xyz_in.shape
@@ -210,7 +213,8 @@ def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=
         ang = torch.empty((S,), dtype=torch.float64, device=dev)
         degen = torch.empty((S,), dtype=torch.int32, device=dev)
         rc = lib.frustum_prepare_batch_f32(_ptr(xyz_in), _ptr(pred), int(n_in), Ns_in, S, int(n_inits), int(seed),
-                                           float(ry_sigma), float(t_amp), _ptr(xyz), _ptr(label), _ptr(n_pts),
+                                           float(ry_sigma), float(t_amp), 1 if sort else 0, _ptr(xyz), _ptr(label),
+                                           _ptr(n_pts),
                                            _ptr(init), _ptr(ang), _ptr(degen), 0, 0, _stream_ptr(stream))
     _native.check(rc, "frustum_prepare_batch")
     return dict(xyz=xyz, label=label, n_pts=n_pts, init=init, init_y_angle=ang, degenerate=degen)

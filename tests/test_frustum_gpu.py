@@ -224,7 +224,8 @@ def test_prepare_matches_initial_guess(cuda):
     smps[4]["pred"] = np.zeros(n, dtype=np.int32)
     xyz_in, pred_in, _ = frustum.pack_clouds(np.stack([s["points"] for s in smps]),
                                              np.stack([s["pred"] for s in smps]))
-    prep = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=seed)
+    prep = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=seed, sort=False)
+    prep_sorted = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=seed, sort=True)
     npts = prep["n_pts"].cpu().numpy()
     for s, smp in enumerate(smps):
         if s == 4:
@@ -237,6 +238,16 @@ def test_prepare_matches_initial_guess(cuda):
         np.testing.assert_array_equal(prep["xyz"][s, :, :npts[s]].cpu().numpy(), pf.astype(np.float32))
         np.testing.assert_array_equal(prep["label"][s, :npts[s]].cpu().numpy(), lf.astype(np.int8))
         assert (prep["label"][s, npts[s]:] == -1).all()
+        # sorted variant: same multiset of points, label-0 block then label-1 block, same inits
+        assert prep_sorted["n_pts"][s].item() == npts[s]
+        xs = prep_sorted["xyz"][s, :, :npts[s]].cpu().numpy()
+        ls_ = prep_sorted["label"][s, :npts[s]].cpu().numpy()
+        assert (np.diff(ls_.astype(np.int32)) >= 0).all()
+        a = np.concatenate([xs, ls_[None].astype(np.float32)], axis=0)
+        b = np.concatenate([pf.astype(np.float32), lf[None].astype(np.float32)], axis=0)
+        np.testing.assert_array_equal(a[:, np.lexsort(a)], b[:, np.lexsort(b)])
+        assert (prep_sorted["label"][s, npts[s]:] == -1).all()
+        np.testing.assert_array_equal(prep_sorted["init"][s].cpu().numpy(), prep["init"][s].cpu().numpy())
         c = philox4x32_10([np.arange(I), np.full(I, s), np.zeros(I), np.zeros(I)], seed & 0xFFFFFFFF, seed >> 32)
         u1 = 1.0 - ((c[0] >> np.uint64(5)).astype(np.float64) * 67108864.0
                     + (c[1] >> np.uint64(6)).astype(np.float64)) / 9007199254740992.0
