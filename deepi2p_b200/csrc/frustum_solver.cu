@@ -571,7 +571,7 @@ struct LMState {
   int ls_iter, evals, ls_steps, term;
 };
 
-constexpr int kRing = 128;               // pending ring per label: < 64 carried + at most 32 appended per group
+constexpr int kRing = 256;               // pending ring per label: < 64 carried + at most 4 x 32 appended per step
 
 template <typename CT, int P>
 struct Smem {
@@ -669,22 +669,20 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
       mask = __ballot_sync(0xffffffffu, box_undecided<0>(box_s + (size_t)r * kBoxRoundFloats, warp * 32 + lane, cc));
 #endif
     }
-    // Undecided groups are fetched four at a time (all loads in flight before the first use),
-    // then classified one by one; draining happens after each group so the rings cannot overflow.
-    CT gx[4], gy[4], gz[4];
-    int glab[4];
-    int gcount = 0, gnext = 0;
+    // Undecided groups are taken four at a time: all loads are issued before the first use and the
+    // four classifications are independent instruction streams; the rings hold < 64 carried
+    // + 128 new entries, and are drained (in batches of 64) after every step.
 #pragma unroll 1
     do {
-      if (gnext == gcount && mask) {
-        gcount = 0; gnext = 0;
+      if (mask) {
+        CT gx[4], gy[4], gz[4];
+        int glab[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
           if (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            ++gcount;
             const int i = (r * kThreads + b * kWarps + warp) * 32 + lane;      // this lane's point
             if (i < n) {
               glab[u] = lab_s[i];
@@ -692,26 +690,22 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
             }
           }
         }
-      }
-      if (gnext < gcount) {
-        // select slot gnext without dynamic register indexing
-        CT px = gx[0], py = gy[0], pz = gz[0];
-        int lab = glab[0];
+        bool mb[4];
 #pragma unroll
-        for (int u = 1; u < 4; ++u)
-          if (gnext == u) { px = gx[u]; py = gy[u]; pz = gz[u]; lab = glab[u]; }
-        ++gnext;
-        const bool mb = maybe_active<P>((float)px, (float)py, (float)pz, lab, cc);
-        const unsigned m1 = __ballot_sync(0xffffffffu, mb && lab == 1);
-        const unsigned m0 = __ballot_sync(0xffffffffu, mb && lab == 0);
-        if (mb) {
-          Entry<CT> e;
-          e.x = px; e.y = py; e.z = pz; e.lab = lab;
-          if (lab) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
-          else     ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
+        for (int u = 0; u < 4; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
+          const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
+          if (mb[u]) {
+            Entry<CT> e;
+            e.x = gx[u]; e.y = gy[u]; e.z = gz[u]; e.lab = glab[u];
+            if (glab[u]) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
+            else         ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
+          }
+          pend0 += __popc(m0);
+          pend1 += __popc(m1);
         }
-        pend0 += __popc(m0);
-        pend1 += __popc(m1);
       }
 #pragma unroll 1
       while (pend0 >= threshold) {
@@ -745,7 +739,7 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         head1 = (head1 + take) & (kRing - 1);
         pend1 -= take;
       }
-    } while (mask || gnext < gcount);
+    } while (mask);
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
@@ -908,7 +902,7 @@ __device__ __noinline__ int poly_roots_real(const double* pin, int n, double* ro
     zr[i] = 0.5 * radius * co; zi[i] = 0.5 * radius * s;
   }
   #pragma unroll 1
-  for (int it = 0; it < 500; ++it) {
+  for (int it = 0; it < 100; ++it) {
     double change = 0.0;
     #pragma unroll 1
     for (int i = 0; i < deg; ++i) {
@@ -932,7 +926,7 @@ __device__ __noinline__ int poly_roots_real(const double* pin, int n, double* ro
       zr[i] -= qr; zi[i] -= qi;
       change = fmax(change, sqrt(qr * qr + qi * qi));
     }
-    if (change < 1e-15 * radius) break;
+    if (change < 1e-14 * radius) break;
   }
   #pragma unroll 1
   for (int i = 0; i < deg; ++i) roots[i] = zr[i];

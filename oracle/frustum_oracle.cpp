@@ -347,7 +347,7 @@ void poly_roots_real(std::vector<double> p, std::vector<double>* real) {
   for (int i = 1; i <= deg; ++i) maxc = std::max(maxc, std::fabs(p[i] / p[0]));
   const double radius = 1.0 + maxc;
   for (int i = 0; i < deg; ++i) z[i] = std::polar(radius * 0.5, 2.0 * M_PI * i / deg + 0.4);
-  for (int it = 0; it < 500; ++it) {
+  for (int it = 0; it < 100; ++it) {
     double change = 0.0;
     for (int i = 0; i < deg; ++i) {
       cd num(0.0, 0.0);
@@ -359,7 +359,7 @@ void poly_roots_real(std::vector<double> p, std::vector<double>* real) {
       z[i] -= dz;
       change = std::max(change, std::abs(dz));
     }
-    if (change < 1e-15 * radius) break;
+    if (change < 1e-14 * radius) break;
   }
   for (int i = 0; i < deg; ++i) real->push_back(z[i].real());
 }
