@@ -589,16 +589,23 @@ struct Smem {
 };
 
 // Box test of one group by one lane: true if the group needs per-point work.
-template <int SMEM>
-__device__ __forceinline__ float box_field(const float* f, int idx) { return SMEM ? f[idx] : __ldg(f + idx); }
+// One box record as seven registers (cx cy cz hx hy hz flags).
+struct BoxRec {
+  float v[7];
+};
 
 template <int SMEM>
-__device__ __forceinline__ bool box_undecided(const float* f, int slot, const ClassConst& cc) {
-  const int flags = __float_as_int(box_field<SMEM>(f, 6 * kThreads + slot));
+__device__ __forceinline__ void box_load(const float* f, int slot, BoxRec& b) {
+#pragma unroll
+  for (int k = 0; k < 7; ++k) b.v[k] = SMEM ? f[k * kThreads + slot] : __ldg(f + k * kThreads + slot);
+}
+
+// Box test of one group by one lane: true if the group needs per-point work.
+__device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst& cc) {
+  const int flags = __float_as_int(b.v[6]);
   if (flags == 0) return false;                       // no point with a residual block
   if (!cc.enabled) return true;
-  const float cx = box_field<SMEM>(f, slot), cy = box_field<SMEM>(f, kThreads + slot), cz = box_field<SMEM>(f, 2 * kThreads + slot);
-  const float hx = box_field<SMEM>(f, 3 * kThreads + slot), hy = box_field<SMEM>(f, 4 * kThreads + slot), hz = box_field<SMEM>(f, 5 * kThreads + slot);
+  const float cx = b.v[0], cy = b.v[1], cz = b.v[2], hx = b.v[3], hy = b.v[4], hz = b.v[5];
   const float m = 2.0f * fmaf(cc.G, (fabsf(cx) + hx) + (fabsf(cy) + hy) + (fabsf(cz) + hz), cc.G0);
   float lo[5], hi[5];
 #pragma unroll
@@ -641,6 +648,12 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
   int head0 = 0, pend0 = 0, head1 = 0, pend1 = 0;   // warp-uniform
   double prod = 1.0;                                  // per-lane product of (1 + s), renormalised
   int expo = 0;
+  BoxRec box_cur, box_nxt;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) { box_cur.v[k] = 0.f; box_nxt.v[k] = 0.f; }
+#if !DIB_BOX_SMEM
+  if (rounds > 0) box_load<0>(box_s, warp * 32 + lane, box_nxt);
+#endif
 
   // Rounds r = 0 .. rounds-1 test one box per lane; the extra last round only drains what is left,
   // so each exact evaluator has ONE code instance.
@@ -664,10 +677,12 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         ++box_phase;
       }
 #if DIB_BOX_SMEM
-      mask = __ballot_sync(0xffffffffu, box_undecided<1>(sm.box[r % kBoxRounds], warp * 32 + lane, cc));
+      box_load<1>(sm.box[r % kBoxRounds], warp * 32 + lane, box_cur);
 #else
-      mask = __ballot_sync(0xffffffffu, box_undecided<0>(box_s + (size_t)r * kBoxRoundFloats, warp * 32 + lane, cc));
+      box_cur = box_nxt;                              // loaded while the previous round was processed
+      if (r + 1 < rounds) box_load<0>(box_s + (size_t)(r + 1) * kBoxRoundFloats, warp * 32 + lane, box_nxt);
 #endif
+      mask = __ballot_sync(0xffffffffu, box_undecided(box_cur, cc));
     }
     // Undecided groups are taken four at a time: all loads are issued before the first use and the
     // four classifications are independent instruction streams; the rings hold < 64 carried
@@ -743,17 +758,21 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
-  // fixed-order reduction: butterfly inside the warp, then warps 0..kWarps-1 in order
+  // Fixed-order reduction.  The pending rings are empty now, so each warp reuses its ring memory as a
+  // [N][33] scratch: lane j sums accumulator j over lanes 0..31 in order, then thread j sums the
+  // warps in order.  (A loop over shared memory instead of ~300 unrolled shuffles: this epilogue
+  // runs once per pass and its code size matters more than its speed.)
+  double* scratch = reinterpret_cast<double*>(sm.list[warp]);
+  static_assert(sizeof(Entry<CT>) * 2 * kRing >= sizeof(double) * N * 33, "ring too small for the reduction scratch");
+  __syncwarp();
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
-    double v = acc[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    acc[j] = v;
-  }
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) sm.red[warp][j] = acc[j];
+  for (int j = 0; j < N; ++j) scratch[j * 33 + lane] = acc[j];
+  __syncwarp();
+  if (lane < N) {
+    double v = 0.0;
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l) v += scratch[lane * 33 + l];
+    sm.red[warp][lane] = v;
   }
   __syncthreads();
   if (tid < N) {
@@ -865,6 +884,57 @@ __device__ double ipow(double x, int k) {
   return v;
 }
 
+// Durand-Kerner iteration for a polynomial of exact degree DEG (coefficients highest first, p[0] != 0).
+// Everything lives in registers (fully unrolled); returns DEG real parts.
+template <int DEG>
+__device__ __noinline__ int durand_kerner(const double* p, double* roots) {
+  double c[DEG + 1], zr[DEG], zi[DEG];
+  const double ip0 = 1.0 / p[0];
+  double maxc = 0.0;
+#pragma unroll
+  for (int i = 0; i <= DEG; ++i) c[i] = p[i] * ip0;
+#pragma unroll
+  for (int i = 1; i <= DEG; ++i) maxc = fmax(maxc, fabs(c[i]));
+  const double radius = 1.0 + maxc;
+#pragma unroll
+  for (int i = 0; i < DEG; ++i) {
+    double s, co;
+    sincos(2.0 * 3.14159265358979323846 * i / DEG + 0.4, &s, &co);
+    zr[i] = 0.5 * radius * co; zi[i] = 0.5 * radius * s;
+  }
+#pragma unroll 1
+  for (int it = 0; it < 100; ++it) {
+    double change = 0.0;
+#pragma unroll
+    for (int i = 0; i < DEG; ++i) {
+      double nr = 0.0, ni = 0.0;
+#pragma unroll
+      for (int k = 0; k <= DEG; ++k) {
+        const double tr = nr * zr[i] - ni * zi[i] + c[k];
+        const double ti = nr * zi[i] + ni * zr[i];
+        nr = tr; ni = ti;
+      }
+      double dr = 1.0, di = 0.0;
+#pragma unroll
+      for (int j = 0; j < DEG; ++j) if (j != i) {
+        const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
+        const double tr = dr * er - di * ei, ti = dr * ei + di * er;
+        dr = tr; di = ti;
+      }
+      double den = dr * dr + di * di;
+      if (den == 0.0) { dr = 1e-300; di = 0.0; den = dr * dr; if (den == 0.0) den = 1e-300; }
+      const double iden = 1.0 / den;
+      const double qr = (nr * dr + ni * di) * iden, qi = (ni * dr - nr * di) * iden;
+      zr[i] -= qr; zi[i] -= qi;
+      change = fmax(change, sqrt(qr * qr + qi * qi));
+    }
+    if (change < 1e-14 * radius) break;
+  }
+#pragma unroll
+  for (int i = 0; i < DEG; ++i) roots[i] = zr[i];
+  return DEG;
+}
+
 // Real parts of all roots of p (n coefficients, highest first; n - 1 <= 4).
 __device__ __noinline__ int poly_roots_real(const double* pin, int n, double* roots) {
   double p[6];
@@ -887,50 +957,10 @@ __device__ __noinline__ int poly_roots_real(const double* pin, int n, double* ro
     } else { roots[0] = -b / (2.0 * a); roots[1] = roots[0]; }
     return 2;
   }
-  // Durand-Kerner on the monic polynomial
-  double zr[5], zi[5], c[6];
-  double maxc = 0.0;
-  #pragma unroll 1
-  for (int i = 0; i <= deg; ++i) c[i] = p[i] / p[0];
-  #pragma unroll 1
-  for (int i = 1; i <= deg; ++i) maxc = fmax(maxc, fabs(c[i]));
-  const double radius = 1.0 + maxc;
-  #pragma unroll 1
-  for (int i = 0; i < deg; ++i) {
-    double s, co;
-    sincos(2.0 * 3.14159265358979323846 * i / deg + 0.4, &s, &co);
-    zr[i] = 0.5 * radius * co; zi[i] = 0.5 * radius * s;
-  }
-  #pragma unroll 1
-  for (int it = 0; it < 100; ++it) {
-    double change = 0.0;
-    #pragma unroll 1
-    for (int i = 0; i < deg; ++i) {
-      double nr = 0.0, ni = 0.0;
-      #pragma unroll 1
-      for (int k = 0; k <= deg; ++k) {
-        const double tr = nr * zr[i] - ni * zi[i] + c[k];
-        const double ti = nr * zi[i] + ni * zr[i];
-        nr = tr; ni = ti;
-      }
-      double dr = 1.0, di = 0.0;
-      #pragma unroll 1
-      for (int j = 0; j < deg; ++j) if (j != i) {
-        const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
-        const double tr = dr * er - di * ei, ti = dr * ei + di * er;
-        dr = tr; di = ti;
-      }
-      double den = dr * dr + di * di;
-      if (den == 0.0) { dr = 1e-300; di = 0.0; den = dr * dr; if (den == 0.0) den = 1e-300; }
-      const double qr = (nr * dr + ni * di) / den, qi = (ni * dr - nr * di) / den;
-      zr[i] -= qr; zi[i] -= qi;
-      change = fmax(change, sqrt(qr * qr + qi * qi));
-    }
-    if (change < 1e-14 * radius) break;
-  }
-  #pragma unroll 1
-  for (int i = 0; i < deg; ++i) roots[i] = zr[i];
-  return deg;
+  // Durand-Kerner on the monic polynomial (all roots, complex), register-resident for the
+  // quartic that the 3-sample interpolation produces; DEG is a compile-time bound.
+  if (deg == 4) return durand_kerner<4>(p, roots);
+  return durand_kerner<3>(p, roots);
 }
 
 // Step size minimising the polynomial that interpolates the line-search samples over
