@@ -16,7 +16,7 @@
 
 namespace dib {
 
-constexpr int kImThreads = 256;
+constexpr int kImThreads = 128;     // 4096 (b, channel-group) CTAs' worth of work stays co-resident: no wave tail
 
 __device__ __forceinline__ uint32_t ordered_bits(float v) {
   const uint32_t b = __float_as_uint(v + 0.0f);   // -0 -> +0 so that -0 == +0 as in float compare
@@ -52,13 +52,27 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
   const float* rows = data + ((size_t)b * C + c0) * N;
 
   if (VEC) {
+    // software pipeline: the loads of iteration i + 1 are in flight while iteration i is scanned
     const int n4 = N >> 2;
-    for (int i = threadIdx.x; i < n4; i += kImThreads) {
-      const int4 kk = __ldg(reinterpret_cast<const int4*>(idx) + i);
-      float4 vv[CPB];
+    int i = threadIdx.x;
+    int4 kk = make_int4(0, 0, 0, 0);
+    float4 vv[CPB];
+    if (i < n4) {
+      kk = __ldg(reinterpret_cast<const int4*>(idx) + i);
 #pragma unroll
       for (int c = 0; c < CPB; ++c)
         if (c < nc) vv[c] = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)c * N) + i);
+    }
+    while (i < n4) {
+      const int inext = i + kImThreads;
+      int4 kn = make_int4(0, 0, 0, 0);
+      float4 vn[CPB];
+      if (inext < n4) {
+        kn = __ldg(reinterpret_cast<const int4*>(idx) + inext);
+#pragma unroll
+        for (int c = 0; c < CPB; ++c)
+          if (c < nc) vn[c] = __ldcs(reinterpret_cast<const float4*>(rows + (size_t)c * N) + inext);
+      }
       const uint32_t n = (uint32_t)i << 2;
 #pragma unroll
       for (int c = 0; c < CPB; ++c) {
@@ -69,6 +83,10 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
           if ((unsigned)kk.w < (unsigned)K) im_consider<CPB>(bestv, bestk, K, c, kk.w, vv[c].w, n + 3);
         }
       }
+      kk = kn;
+#pragma unroll
+      for (int c = 0; c < CPB; ++c) vv[c] = vn[c];
+      i = inext;
     }
   } else {
     for (int i = threadIdx.x; i < N; i += kImThreads) {
@@ -87,9 +105,34 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
 }
 
 constexpr int kBqWarps = 8;
-constexpr int kBqUnroll = 16;
+constexpr int kBqUnroll = 32;       // 4 KB per warp in flight
 
-// One warp per (b,m) row.
+// One warp per (b,m) row.  Two register buffers of kBqHalf loads per lane: the next 512 elements are
+// in flight while the current 512 are compacted.
+constexpr int kBqHalf = kBqUnroll / 2;
+
+__device__ __forceinline__ void bq_load(const float* d, int base, int N, int lane, float v[kBqHalf]) {
+#pragma unroll
+  for (int j = 0; j < kBqHalf; ++j) {
+    const int n = base + j * 32 + lane;
+    v[j] = (n < N) ? __ldcs(d + n) : __int_as_float(0x7fc00000);   // NaN never hits
+  }
+}
+
+__device__ __forceinline__ void bq_scan(const float v[kBqHalf], float radius, int base, int lane, int K, int32_t* o,
+                                        int& cnt) {
+#pragma unroll
+  for (int j = 0; j < kBqHalf; ++j) {
+    const bool hit = v[j] <= radius;
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+      if (pos < K) o[pos] = base + j * 32 + lane;
+    }
+    cnt += __popc(m);
+  }
+}
+
 __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* __restrict__ dist, float radius,
                                                                    int32_t* __restrict__ out, long long rows, int N,
                                                                    int K) {
@@ -98,24 +141,16 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* 
   if (row >= rows) return;
   const float* d = dist + (size_t)row * N;
   int32_t* o = out + (size_t)row * K;
+  constexpr int kStep = 32 * kBqHalf;
   int cnt = 0;
-  for (int base = 0; base < N && cnt < K; base += 32 * kBqUnroll) {
-    float v[kBqUnroll];
-#pragma unroll
-    for (int j = 0; j < kBqUnroll; ++j) {
-      const int n = base + j * 32 + lane;
-      v[j] = (n < N) ? __ldcs(d + n) : __int_as_float(0x7fc00000);   // NaN never hits
-    }
-#pragma unroll
-    for (int j = 0; j < kBqUnroll; ++j) {
-      const bool hit = v[j] <= radius;
-      const unsigned m = __ballot_sync(0xffffffffu, hit);
-      if (hit) {
-        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-        if (pos < K) o[pos] = base + j * 32 + lane;
-      }
-      cnt += __popc(m);
-    }
+  float va[kBqHalf], vb[kBqHalf];
+  bq_load(d, 0, N, lane, va);
+  for (int base = 0; base < N && cnt < K; base += 2 * kStep) {
+    if (base + kStep < N) bq_load(d, base + kStep, N, lane, vb);
+    bq_scan(va, radius, base, lane, K, o, cnt);
+    if (cnt >= K || base + kStep >= N) break;
+    if (base + 2 * kStep < N) bq_load(d, base + 2 * kStep, N, lane, va);
+    bq_scan(vb, radius, base + kStep, lane, K, o, cnt);
   }
   __syncwarp();
   if (cnt == 0) {
