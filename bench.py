@@ -162,7 +162,8 @@ def cpu_registrations(first_id, count, n_points, n_inits, is_2d, threads):
         costs = np.array([x[1] for x in o])
         best = int(np.argmin(costs))
         res.append(dict(sample=per[c][0], pf=per[c][1], lf=per[c][2], ry=per[c][3], t=per[c][4], P=o[best][0],
-                        cost=float(costs[best]), evals=sum(x[3]["unique_evals"] for x in o)))
+                        cost=float(costs[best]), evals=sum(x[3]["unique_evals"] for x in o),
+                        params=np.stack([x[4] for x in o]), costs=costs))
     return res, dt
 
 
@@ -383,20 +384,41 @@ def main():
         count = max(args.cpu_samples, cpu_batch_size(cores, n_inits))
         cpu, dt = cpu_registrations(rank * S_local, count, n_points, n_inits, is_2d, cores)
         worst_r = worst_t = 0.0
+        d_all, reg_ok, cost_le = [], 0, 0
+        Pn = 4 if is_2d else 6
         for r in cpu:
             xyz1, lab1, np1 = frustum.pack_clouds(r["pf"], r["lf"])
             init = np.concatenate([r["ry"][:, None], r["t"]], axis=1)[None]
-            g = frustum.solve_batch(xyz1, lab1, np1, r["sample"]["K"], init, H, W, max_iter=500, is_2d=is_2d)
+            g = frustum.solve_batch(xyz1, lab1, np1, r["sample"]["K"], init, H, W, max_iter=500, is_2d=is_2d,
+                                    return_all=True)
             Pg = g["P"][0].cpu().numpy()
             c = (np.trace(Pg[:3, :3].T @ r["P"][:3, :3]) - 1.0) / 2.0
-            worst_r = max(worst_r, math.acos(max(-1.0, min(1.0, c))))
-            worst_t = max(worst_t, float(np.linalg.norm(Pg[:3, 3] - r["P"][:3, 3])))
+            er = math.acos(max(-1.0, min(1.0, c)))
+            et = float(np.linalg.norm(Pg[:3, 3] - r["P"][:3, 3]))
+            worst_r, worst_t = max(worst_r, er), max(worst_t, et)
+            reg_ok += int(er < 1e-4 and et < 1e-3)
+            cost_le += int(float(g["cost"][0]) <= r["cost"] * (1 + 1e-9))
+            gp = g["params"][0].cpu().numpy()
+            nr = Pn - 3
+            d_rot = np.linalg.norm(gp[:, :nr] - r["params"][:, :nr], axis=1)
+            d_tr = np.linalg.norm(gp[:, nr:Pn] - r["params"][:, nr:Pn], axis=1)
+            d_all.append(np.stack([d_rot, d_tr], axis=1))
+        d_all = np.concatenate(d_all)
+        within = (d_all[:, 0] < 1e-4) & (d_all[:, 1] < 1e-3)
         line["cpu_baseline"] = {
             "value": count / dt, "unit": "registrations/s", "cores": cores, "kind": "port",
             "sample": "%d registrations x %d inits of the same workload (first samples of the GPU batch), oracle port "
                       "of the Ceres path, all solves spread over %d threads" % (count, n_inits, cores)}
-        line["parity"] = {"max_rot_err_rad": worst_r, "max_trans_err_m": worst_t, "samples": count,
-                          "gate": "1e-4 rad / 1e-3 m vs the CPU oracle (Ceres unavailable offline)"}
+        line["parity"] = {
+            "gate": "1e-4 rad / 1e-3 m vs the CPU oracle (Ceres unavailable offline)",
+            "solves": int(within.size), "solves_within_gate": int(within.sum()),
+            "solve_median_rot_rad": float(np.median(d_all[:, 0])), "solve_median_trans_m": float(np.median(d_all[:, 1])),
+            "solve_max_rot_rad": float(d_all[:, 0].max()), "solve_max_trans_m": float(d_all[:, 1].max()),
+            "registrations": count, "registrations_within_gate": reg_ok,
+            "registrations_gpu_cost_le_oracle": cost_le,
+            "best_of_I_max_rot_err_rad": worst_r, "best_of_I_max_trans_err_m": worst_t,
+            "note": "trajectories are chaotic at rounding level: the CPU oracle against itself with an equivalent "
+                    "linear solver differs in ~3-4 % of solves (scripts/parity_sensitivity_cpu.py)"}
 
     if args.ops:
         line["ops"] = bench_ops(torch, dev, peak)

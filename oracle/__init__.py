@@ -94,6 +94,31 @@ def evaluate(points, labels, K, x, H, W, is_2d=True):
     return cost.value, g, JtJ
 
 
+def residuals(points, labels, K, x, H, W, is_2d=True):
+    """Loss-corrected residual vector at parameter vector x (what Problem::Evaluate returns,
+    registration.cpp:150-155)."""
+    lib = _lib("libfrustum_oracle.so")
+    pts = _prep_points(points)
+    n = pts.shape[1]
+    lab = np.ascontiguousarray(np.asarray(labels).astype(np.int32))
+    K9 = np.ascontiguousarray(np.asarray(K, dtype=np.float64).reshape(9))
+    P = 4 if is_2d else 6
+    xx = np.zeros(6)
+    xx[:P] = np.asarray(x, dtype=np.float64)[:P]
+    lib.frustum_oracle_num_residuals.restype = ctypes.c_int64
+    rows = lib.frustum_oracle_num_residuals(_p(lab, ctypes.c_int32), ctypes.c_int64(n))
+    res = np.zeros(rows)
+    cost = ctypes.c_double(0.0)
+    g = np.zeros(P)
+    JtJ = np.zeros((P, P))
+    lib.frustum_oracle_evaluate(
+        _p(pts, ctypes.c_double), _p(lab, ctypes.c_int32), ctypes.c_int64(n), _p(K9, ctypes.c_double),
+        _p(xx, ctypes.c_double), ctypes.c_double(float(H)), ctypes.c_double(float(W)),
+        ctypes.c_int(1 if is_2d else 0), ctypes.byref(cost), _p(g, ctypes.c_double),
+        _p(JtJ, ctypes.c_double), _p(res, ctypes.c_double))
+    return res, cost.value
+
+
 def wrap_in_pi(x):
     """registration_lsq.py:189-193."""
     x = math.fmod(x + math.pi, math.pi * 2)
