@@ -343,3 +343,53 @@ def test_full_size_properties(cuda):
     # one oracle cross-check at full size
     ms = oracle.solve(smps[0]["points"], smps[0]["pred"], K, inits[0, 0, 0], inits[0, 0, 1:4], H, W, syn.T_LB, syn.T_UB)
     assert abs(params[0, 0, 0] - ms[4][0]) < ROT_TOL and np.linalg.norm(params[0, 0, 1:4] - ms[4][1:4]) < TRANS_TOL
+
+
+def test_f64_coordinates_solve(cuda):
+    """Coordinates that are not float32-representable take the f64 device record end to end."""
+    smp = small_sample(21, 3000)
+    rng = np.random.default_rng(3)
+    pts = smp["points"].astype(np.float64) + rng.normal(0, 1e-7, smp["points"].shape)
+    xyz, lab, n_pts = frustum.pack_clouds(pts, smp["pred"])
+    assert xyz.dtype == torch.float64
+    iy, _, _, _ = oracle.initial_guess(pts, smp["pred"])
+    ry, t = syn.make_inits(21, iy, 4)
+    init = np.concatenate([ry[:, None], t], axis=1)[None]
+    out = frustum.solve_batch(xyz, lab, n_pts, smp["K"], init, smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500, True,
+                              return_all=True)
+    ok = 0
+    for i in range(4):
+        _, co, _, st, xo = oracle.solve(pts, smp["pred"], smp["K"], ry[i], t[i], smp["H"], smp["W"], syn.T_LB, syn.T_UB)
+        p = out["params"][0, i].cpu().numpy()
+        ok += int(abs(p[0] - xo[0]) < ROT_TOL and np.linalg.norm(p[1:4] - xo[1:4]) < TRANS_TOL)
+        c_at = oracle.evaluate(pts, smp["pred"], smp["K"], p[:4], smp["H"], smp["W"], True)[0]
+        assert abs(out["costs"][0, i].item() - c_at) <= 1e-9 * max(1.0, c_at)
+    assert ok >= 3
+
+
+def test_large_cloud_unsorted_fallback_and_oxford_6dof(cuda):
+    """(a) a cloud larger than the in-shared-memory sort window (32768 points) goes through prepare
+    unsorted and through the solver's multi-chunk box table; (b) Oxford-shaped intrinsics, 6-DoF."""
+    n = 40000
+    smp = syn.make_sample(31, n_points=n, shape="oxford")
+    xyz_in, pred_in, _ = frustum.pack_clouds(smp["points"], smp["pred"])
+    prep = frustum.prepare_batch(xyz_in, pred_in, n, 3, seed=5)
+    iy, pf, lf, mask = oracle.initial_guess(smp["points"], smp["pred"])
+    m = int(prep["n_pts"][0])
+    assert m == mask.sum()
+    np.testing.assert_array_equal(prep["xyz"][0, :, :m].cpu().numpy(), pf.astype(np.float32))   # original order kept
+    for is_2d in (True, False):
+        out = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], smp["K"], prep["init"], smp["H"],
+                                  smp["W"], syn.T_LB, syn.T_UB, 500, is_2d, return_all=True)
+        ini = prep["init"][0].cpu().numpy()
+        ok = 0
+        for i in range(3):
+            _, co, _, st, xo = oracle.solve(pf, lf, smp["K"], ini[i, 0], ini[i, 1:4], smp["H"], smp["W"], syn.T_LB,
+                                            syn.T_UB, 500, is_2d)
+            P = 4 if is_2d else 6
+            p = out["params"][0, i].cpu().numpy()
+            nr = P - 3
+            ok += int(np.linalg.norm(p[:nr] - xo[:nr]) < ROT_TOL and np.linalg.norm(p[nr:P] - xo[nr:P]) < TRANS_TOL)
+            c_at = oracle.evaluate(pf, lf, smp["K"], p[:P], smp["H"], smp["W"], is_2d)[0]
+            assert abs(out["costs"][0, i].item() - c_at) <= 1e-9 * max(1.0, c_at)
+        assert ok >= 2
