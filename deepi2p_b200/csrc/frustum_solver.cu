@@ -890,12 +890,17 @@ template <int DEG>
 __device__ __noinline__ int durand_kerner(const double* p, double* roots) {
   double c[DEG + 1], zr[DEG], zi[DEG];
   const double ip0 = 1.0 / p[0];
-  double maxc = 0.0;
 #pragma unroll
   for (int i = 0; i <= DEG; ++i) c[i] = p[i] * ip0;
+  // Fujiwara's bound on the root moduli: 2 max_k |c_k|^(1/k) (the last coefficient halved)
+  double radius = 0.0;
 #pragma unroll
-  for (int i = 1; i <= DEG; ++i) maxc = fmax(maxc, fabs(c[i]));
-  const double radius = 1.0 + maxc;
+  for (int i = 1; i <= DEG; ++i) {
+    const double a = fabs(c[i]) * (i == DEG ? 0.5 : 1.0);
+    radius = fmax(radius, a > 0.0 ? exp(log(a) / (double)i) : 0.0);
+  }
+  radius = 2.0 * radius + 1e-300;
+  // start points on the circle of half that radius, fixed phases (cos/sin of 2 pi i / DEG + 0.4)
 #pragma unroll
   for (int i = 0; i < DEG; ++i) {
     double s, co;
@@ -980,14 +985,18 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
   int row = 0;
   #pragma unroll 1
   for (int i = 0; i < ns; ++i) {
+    double pw[6];                       // pw[k] = x^k by repeated multiplication
+    pw[0] = 1.0;
+    #pragma unroll 1
+    for (int k = 1; k <= deg; ++k) pw[k] = pw[k - 1] * s[i]->x;
     if (s[i]->value_valid) {
       #pragma unroll 1
-      for (int j = 0; j <= deg; ++j) M[row][j] = ipow(s[i]->x, deg - j);
+      for (int j = 0; j <= deg; ++j) M[row][j] = pw[deg - j];
       rhs[row] = s[i]->value; ++row;
     }
     if (s[i]->gradient_valid) {
       #pragma unroll 1
-      for (int j = 0; j < deg; ++j) M[row][j] = (deg - j) * ipow(s[i]->x, deg - j - 1);
+      for (int j = 0; j < deg; ++j) M[row][j] = (deg - j) * pw[deg - j - 1];
       rhs[row] = s[i]->gradient; ++row;
     }
   }

@@ -343,9 +343,13 @@ void poly_roots_real(std::vector<double> p, std::vector<double>* real) {
   }
   typedef std::complex<double> cd;
   std::vector<cd> z(deg);
-  double maxc = 0.0;
-  for (int i = 1; i <= deg; ++i) maxc = std::max(maxc, std::fabs(p[i] / p[0]));
-  const double radius = 1.0 + maxc;
+  // Fujiwara's bound on the root moduli: 2 max_k |c_k|^(1/k) (the last coefficient halved)
+  double radius = 0.0;
+  for (int i = 1; i <= deg; ++i) {
+    const double a = std::fabs(p[i] / p[0]) * (i == deg ? 0.5 : 1.0);
+    radius = std::max(radius, a > 0.0 ? std::exp(std::log(a) / (double)i) : 0.0);
+  }
+  radius = 2.0 * radius + 1e-300;
   for (int i = 0; i < deg; ++i) z[i] = std::polar(radius * 0.5, 2.0 * M_PI * i / deg + 0.4);
   for (int it = 0; it < 100; ++it) {
     double change = 0.0;
