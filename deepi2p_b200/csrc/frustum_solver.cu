@@ -34,7 +34,7 @@ void set_error(const char* fmt, ...) {
 #define DIB_THREADS 64
 #endif
 #ifndef DIB_MINBLOCKS4
-#define DIB_MINBLOCKS4 8
+#define DIB_MINBLOCKS4 10
 #endif
 #ifndef DIB_MINBLOCKS6
 #define DIB_MINBLOCKS6 6
@@ -480,6 +480,13 @@ constexpr int kBoxRoundFloats = kBoxFields * kThreads;
 #ifndef DIB_BOX_ROUNDS
 #define DIB_BOX_ROUNDS 8
 #endif
+#ifndef DIB_GPS
+#define DIB_GPS 4                             // undecided groups fetched + classified per step
+#endif
+#ifndef DIB_EXACT_ILP
+#define DIB_EXACT_ILP 1                       // exact-path entries per lane per batch (1 or 2); 1 fits 96 registers
+                                              // -> 10 CTAs/SM, measured faster than ILP 2 at 8 CTAs/SM
+#endif
 #ifndef DIB_BOX_SMEM
 #define DIB_BOX_SMEM 0                        // 1: table bulk-copied (TMA engine) into shared memory per problem; 0: read via L1/L2
                                               // (measured faster on B200: profiles/r01_sweep_build_params.jsonl)
@@ -571,7 +578,9 @@ struct LMState {
   int ls_iter, evals, ls_steps, term;
 };
 
-constexpr int kRing = 256;               // pending ring per label: < 64 carried + at most 4 x 32 appended per step
+constexpr int kBatch = 32 * DIB_EXACT_ILP;   // entries evaluated per exact-path batch
+constexpr int kRing = 256;               // pending ring per label: < kBatch carried + at most DIB_GPS x 32 appended per step
+static_assert(kBatch + 32 * DIB_GPS <= kRing, "ring too small");
 
 template <typename CT, int P>
 struct Smem {
@@ -662,7 +671,7 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
     unsigned mask = 0;
     int threshold = 1;
     if (r < rounds) {
-      threshold = 64;
+      threshold = kBatch;
       if (DIB_BOX_SMEM && !boxes_resident && (r % kBoxRounds) == 0) {
         // clouds larger than the resident window: stream the table chunk by chunk, every pass
         __syncthreads();
@@ -690,10 +699,10 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
 #pragma unroll 1
     do {
       if (mask) {
-        CT gx[4], gy[4], gz[4];
-        int glab[4];
+        CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+        int glab[DIB_GPS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DIB_GPS; ++u) {
           glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
           if (mask) {
             const int b = __ffs(mask) - 1;
@@ -705,11 +714,11 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
             }
           }
         }
-        bool mb[4];
+        bool mb[DIB_GPS];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
+        for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < DIB_GPS; ++u) {
           const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
           const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
           if (mb[u]) {
@@ -725,32 +734,46 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
 #pragma unroll 1
       while (pend0 >= threshold) {
         __syncwarp();
-        const int take = pend0 < 64 ? pend0 : 64;
+        const int take = pend0 < kBatch ? pend0 : kBatch;
         const Entry<CT> ea = ring0[(head0 + lane) & (kRing - 1)];
-        const Entry<CT> eb = ring0[(head0 + 32 + lane) & (kRing - 1)];
-        Out0<P> oa, ob;
+        Out0<P> oa;
         eval_outside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
+#if DIB_EXACT_ILP == 2
+        const Entry<CT> eb = ring0[(head0 + 32 + lane) & (kRing - 1)];
+        Out0<P> ob;
         eval_outside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
         prod *= oa.s1 * ob.s1;
+#else
+        prod *= oa.s1;
+#endif
         renorm_product(prod, expo);
         rank1<P>(acc, oa.J, oa.w, oa.r);
+#if DIB_EXACT_ILP == 2
         rank1<P>(acc, ob.J, ob.w, ob.r);
+#endif
         head0 = (head0 + take) & (kRing - 1);
         pend0 -= take;
       }
 #pragma unroll 1
       while (pend1 >= threshold) {
         __syncwarp();
-        const int take = pend1 < 64 ? pend1 : 64;
+        const int take = pend1 < kBatch ? pend1 : kBatch;
         const Entry<CT> ea = ring1[(head1 + lane) & (kRing - 1)];
-        const Entry<CT> eb = ring1[(head1 + 32 + lane) & (kRing - 1)];
-        Out1<P> oa, ob;
+        Out1<P> oa;
         eval_inside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
+#if DIB_EXACT_ILP == 2
+        const Entry<CT> eb = ring1[(head1 + 32 + lane) & (kRing - 1)];
+        Out1<P> ob;
         eval_inside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
         prod *= oa.s1 * ob.s1;
+#else
+        prod *= oa.s1;
+#endif
         renorm_product(prod, expo);
         accumulate_inside<P>(acc, oa);
+#if DIB_EXACT_ILP == 2
         accumulate_inside<P>(acc, ob);
+#endif
         head1 = (head1 + take) & (kRing - 1);
         pend1 -= take;
       }
