@@ -576,6 +576,7 @@ struct LMState {
   int reuse_diag, step_ok, invalid, iteration, max_iter;
   int phase;             // 0 initial, 1 line-search sample, 2 candidate after failed line search
   int ls_iter, evals, ls_steps, term;
+  double scratch[72];    // line-search interpolation workspace (shared memory, see interpolating_min_step)
 };
 
 constexpr int kBatch = 32 * DIB_EXACT_ILP;   // entries evaluated per exact-path batch
@@ -993,8 +994,10 @@ __device__ __noinline__ int poly_roots_real(const double* pin, int n, double* ro
 
 // Step size minimising the polynomial that interpolates the line-search samples over
 // [xmin, xmax] (cubic interpolation: values and gradients of lower / current / previous).
+// `scratch` (>= 72 doubles, shared memory): the dynamically indexed 6x6 system must not live in
+// local memory, whose lines get evicted from L1 by the streaming loads (long-scoreboard stalls).
 __device__ __noinline__ double interpolating_min_step(const LsSample& lower, const LsSample& previous, const LsSample& current,
-                                         double xmin, double xmax) {
+                                         double xmin, double xmax, double* scratch) {
   if (!current.value_valid) return fmin(fmax(current.x * 0.5, xmin), xmax);
   const LsSample* s[3] = {&lower, &current, &previous};
   const int ns = previous.value_valid ? 3 : 2;
@@ -1002,14 +1005,19 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
   #pragma unroll 1
   for (int i = 0; i < ns; ++i) { if (s[i]->value_valid) ++nc; if (s[i]->gradient_valid) ++nc; }
   const int deg = nc - 1;
-  double M[6][6], rhs[6], poly[6];
+  double (*M)[6] = reinterpret_cast<double (*)[6]>(scratch);   // [6][6]
+  double* rhs = scratch + 36;
+  double* poly = scratch + 42;
+  double* z = scratch + 48;
+  double* der = scratch + 54;
+  double* roots = scratch + 60;
+  double* pw = scratch + 66;
   #pragma unroll 1
   for (int i = 0; i < 6; ++i) { rhs[i] = 0; poly[i] = 0; for (int j = 0; j < 6; ++j) M[i][j] = 0; }
   int row = 0;
   #pragma unroll 1
   for (int i = 0; i < ns; ++i) {
-    double pw[6];                       // pw[k] = x^k by repeated multiplication
-    pw[0] = 1.0;
+    pw[0] = 1.0;                        // pw[k] = x^k by repeated multiplication
     #pragma unroll 1
     for (int k = 1; k <= deg; ++k) pw[k] = pw[k - 1] * s[i]->x;
     if (s[i]->value_valid) {
@@ -1023,10 +1031,8 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
       rhs[row] = s[i]->gradient; ++row;
     }
   }
-  // full-pivot elimination
-  int perm[6];
-  #pragma unroll 1
-  for (int i = 0; i < nc; ++i) perm[i] = i;
+  // full-pivot elimination (column permutation packed in one register, 4 bits per entry)
+  unsigned perm = 0x543210u;
   #pragma unroll 1
   for (int k = 0; k < nc; ++k) {
     int pr = k, pcv = k; double best = -1.0;
@@ -1035,7 +1041,8 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
       if (fabs(M[i][j]) > best) { best = fabs(M[i][j]); pr = i; pcv = j; }
     if (best == 0.0) { for (int i = k; i < nc; ++i) rhs[i] = 0.0; break; }
     if (pr != k) { for (int j = 0; j < nc; ++j) { double t = M[pr][j]; M[pr][j] = M[k][j]; M[k][j] = t; } double t = rhs[pr]; rhs[pr] = rhs[k]; rhs[k] = t; }
-    if (pcv != k) { for (int i = 0; i < nc; ++i) { double t = M[i][pcv]; M[i][pcv] = M[i][k]; M[i][k] = t; } int t = perm[pcv]; perm[pcv] = perm[k]; perm[k] = t; }
+    if (pcv != k) { for (int i = 0; i < nc; ++i) { double t = M[i][pcv]; M[i][pcv] = M[i][k]; M[i][k] = t; } const unsigned pa = (perm >> (4 * pcv)) & 15u, pb = (perm >> (4 * k)) & 15u;
+                    perm = (perm & ~((15u << (4 * pcv)) | (15u << (4 * k)))) | (pb << (4 * pcv)) | (pa << (4 * k)); }
     #pragma unroll 1
     for (int i = k + 1; i < nc; ++i) {
       const double f = M[i][k] / M[k][k];
@@ -1044,7 +1051,6 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
       rhs[i] -= f * rhs[k];
     }
   }
-  double z[6];
   #pragma unroll 1
   for (int k = nc - 1; k >= 0; --k) {
     if (M[k][k] == 0.0) { z[k] = 0.0; continue; }
@@ -1054,7 +1060,7 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
     z[k] = sacc / M[k][k];
   }
   #pragma unroll 1
-  for (int k = 0; k < nc; ++k) poly[perm[k]] = z[k];
+  for (int k = 0; k < nc; ++k) poly[(perm >> (4 * k)) & 15u] = z[k];
 
   double best_x = (xmin + xmax) / 2.0;
   double best_v = poly_eval(poly, nc, best_x);
@@ -1063,7 +1069,6 @@ __device__ __noinline__ double interpolating_min_step(const LsSample& lower, con
   const double vmax = poly_eval(poly, nc, xmax);
   if (vmax < best_v) { best_v = vmax; best_x = xmax; }
   if (nc <= 2) return best_x;
-  double der[6], roots[5];
   #pragma unroll 1
   for (int j = 0; j < deg; ++j) der[j] = (deg - j) * poly[j];
   const int nr = poly_roots_real(der, deg, roots);
@@ -1227,7 +1232,7 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
     bool fail = st.ls_iter >= 20;
     double a = 0.0;
     if (!fail) {
-      a = interpolating_min_step(st.lower, st.prev, cur, 1e-3 * cur.x, 0.6 * cur.x);
+      a = interpolating_min_step(st.lower, st.prev, cur, 1e-3 * cur.x, 0.6 * cur.x, st.scratch);
       if (a * st.dmax < 1e-9) fail = true;
     }
     if (fail) {
