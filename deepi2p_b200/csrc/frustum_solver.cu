@@ -481,7 +481,7 @@ constexpr int kBoxRoundFloats = kBoxFields * kThreads;
 #define DIB_BOX_ROUNDS 8
 #endif
 #ifndef DIB_GPS
-#define DIB_GPS 4                             // undecided groups fetched + classified per step
+#define DIB_GPS 2                             // undecided groups fetched + classified per step
 #endif
 #ifndef DIB_EXACT_ILP
 #define DIB_EXACT_ILP 1                       // exact-path entries per lane per batch (1 or 2); 1 fits 96 registers
@@ -694,14 +694,15 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
 #endif
       mask = __ballot_sync(0xffffffffu, box_undecided(box_cur, cc));
     }
-    // Undecided groups are taken four at a time: all loads are issued before the first use and the
-    // four classifications are independent instruction streams; the rings hold < 64 carried
-    // + 128 new entries, and are drained (in batches of 64) after every step.
+    // Undecided groups are taken DIB_GPS at a time.  Their loads are issued first, then the pending
+    // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
+    // (independent instruction streams) and appended.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
 #pragma unroll 1
     do {
-      if (mask) {
-        CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-        int glab[DIB_GPS];
+      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+      int glab[DIB_GPS];
+      const bool have = mask != 0;
+      if (have) {
 #pragma unroll
         for (int u = 0; u < DIB_GPS; ++u) {
           glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
@@ -714,22 +715,6 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
               gx[u] = xyz_s[i]; gy[u] = xyz_s[n_stride + i]; gz[u] = xyz_s[2 * (size_t)n_stride + i];
             }
           }
-        }
-        bool mb[DIB_GPS];
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) {
-          const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
-          const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
-          if (mb[u]) {
-            Entry<CT> e;
-            e.x = gx[u]; e.y = gy[u]; e.z = gz[u]; e.lab = glab[u];
-            if (glab[u]) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
-            else         ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
-          }
-          pend0 += __popc(m0);
-          pend1 += __popc(m1);
         }
       }
 #pragma unroll 1
@@ -778,6 +763,24 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         head1 = (head1 + take) & (kRing - 1);
         pend1 -= take;
       }
+      if (have) {
+        bool mb[DIB_GPS];
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) {
+          const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
+          const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
+          if (mb[u]) {
+            Entry<CT> e;
+            e.x = gx[u]; e.y = gy[u]; e.z = gz[u]; e.lab = glab[u];
+            if (glab[u]) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
+            else         ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
+          }
+          pend0 += __popc(m0);
+          pend1 += __popc(m1);
+        }
+            }
     } while (mask);
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
