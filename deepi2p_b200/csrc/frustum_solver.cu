@@ -35,7 +35,7 @@ void set_error(const char* fmt, ...) {
 #define DIB_THREADS 64
 #endif
 #ifndef DIB_MINBLOCKS4
-#define DIB_MINBLOCKS4 10
+#define DIB_MINBLOCKS4 9                          // 112 registers, no spills (10 -> 96 registers with spills: slower)
 #endif
 #ifndef DIB_MINBLOCKS6
 #define DIB_MINBLOCKS6 6
@@ -1554,6 +1554,11 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   if (const char* e = getenv("DIB_CHUNK_SAMPLES")) chunk = atoll(e);   // tuning knob
   if (chunk < 1) chunk = 1;
   if (chunk > a.S) chunk = a.S;
+  {
+    // equal-sized chunks: a short last chunk would bring the tail back
+    const long long nchunks = (a.S + chunk - 1) / chunk;
+    chunk = (a.S + nchunks - 1) / nchunks;
+  }
   a.chunk = (int)chunk;
   kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
   DIB_CHECK_CUDA(cudaGetLastError());
