@@ -35,7 +35,8 @@ void set_error(const char* fmt, ...) {
 #define DIB_THREADS 64
 #endif
 #ifndef DIB_MINBLOCKS4
-#define DIB_MINBLOCKS4 9                          // 112 registers, no spills (10 -> 96 registers with spills: slower)
+#define DIB_MINBLOCKS4 10                         // ptxas settles on 96 registers (~60 B of spills) for both 9 and 10;
+                                              // 8 (124 registers, no spills, 16 warps/SM) measured slower
 #endif
 #ifndef DIB_MINBLOCKS6
 #define DIB_MINBLOCKS6 6
