@@ -23,15 +23,19 @@ __device__ __forceinline__ uint32_t ordered_bits(float v) {
   return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
 }
 
+// Common path: one shared-memory load and one float compare.  bestf is only a FILTER: it is updated
+// with plain (racy) stores, so it may lag behind the true running maximum, which merely lets a few
+// extra candidates through; the winner is decided by the 64-bit atomicMax on bestk alone.
+// `>=` lets equal values through (a tie must still be able to win with a lower n); NaN fails it.
 template <int CPB>
-__device__ __forceinline__ void im_consider(uint32_t* bestv, unsigned long long* bestk, int K, int c, int k,
+__device__ __forceinline__ void im_consider(float* bestf, unsigned long long* bestk, int K, int c, int k,
                                             float v, uint32_t n) {
-  if (!(v > -1000.0f)) return;                    // also rejects NaN
-  const uint32_t ord = ordered_bits(v);
-  uint32_t* pv = bestv + c * K + k;
-  if (ord >= *pv) {
-    atomicMax(pv, ord);
-    atomicMax(bestk + c * K + k, ((unsigned long long)ord << 32) | (unsigned long long)(0xFFFFFFFFu - n));
+  float* pf = bestf + c * K + k;
+  if (v >= *pf) {
+    if (!(v > -1000.0f)) return;                  // the floor itself never wins (strict > in the reference)
+    *pf = v;
+    atomicMax(bestk + c * K + k,
+              ((unsigned long long)ordered_bits(v) << 32) | (unsigned long long)(0xFFFFFFFFu - n));
   }
 }
 
@@ -42,11 +46,11 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
                                                                int32_t* __restrict__ out, int B, int C, int N, int K) {
   extern __shared__ __align__(16) unsigned char im_smem[];
   unsigned long long* bestk = reinterpret_cast<unsigned long long*>(im_smem);
-  uint32_t* bestv = reinterpret_cast<uint32_t*>(bestk + (size_t)CPB * K);
+  float* bestv = reinterpret_cast<float*>(bestk + (size_t)CPB * K);
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CPB;
   const int nc = min(CPB, C - c0);
-  for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = 0u; }
+  for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = -1000.0f; }
   __syncthreads();
   const int32_t* idx = index + (size_t)b * N;
   const float* rows = data + ((size_t)b * C + c0) * N;
@@ -160,6 +164,53 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* 
   }
 }
 
+// Row split over the 4 warps of a CTA (one CTA per row): each warp compacts its quarter of the row
+// into its own shared-memory list (at most K hits), then the lists are concatenated in order.  Four
+// times as many independent load streams as the warp-per-row kernel; used when 4 K ints fit in
+// shared memory.  A later quarter cannot know that earlier quarters already hold K hits, so rows
+// whose K-th hit comes early read more than they strictly need.
+constexpr int kBqSplit = 4;
+
+__global__ void __launch_bounds__(kBqSplit * 32) ball_query_split_kernel(const float* __restrict__ dist, float radius,
+                                                                         int32_t* __restrict__ out, int N, int K) {
+  extern __shared__ int32_t bq_hits[];          // [kBqSplit][K]
+  __shared__ int bq_cnt[kBqSplit];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const float* d = dist + (size_t)blockIdx.x * N;
+  int32_t* o = out + (size_t)blockIdx.x * K;
+  // quarter boundaries on multiples of 32 elements
+  const int per = (((N + kBqSplit - 1) / kBqSplit) + 31) & ~31;
+  const int lo = min(w * per, N), hi = min(lo + per, N);
+  int32_t* mine = bq_hits + w * K;
+  constexpr int kStep = 32 * kBqHalf;
+  int cnt = 0;
+  float va[kBqHalf], vb[kBqHalf];
+  if (lo < hi) {
+    bq_load(d, lo, hi, lane, va);
+    for (int base = lo; base < hi && cnt < K; base += 2 * kStep) {
+      if (base + kStep < hi) bq_load(d, base + kStep, hi, lane, vb);
+      bq_scan(va, radius, base, lane, K, mine, cnt);
+      if (cnt >= K || base + kStep >= hi) break;
+      if (base + 2 * kStep < hi) bq_load(d, base + 2 * kStep, hi, lane, va);
+      bq_scan(vb, radius, base + kStep, lane, K, mine, cnt);
+    }
+  }
+  if (lane == 0) bq_cnt[w] = min(cnt, K);
+  __syncthreads();
+  int start = 0, total = 0;
+#pragma unroll
+  for (int q = 0; q < kBqSplit; ++q) { if (q < w) start += bq_cnt[q]; total += bq_cnt[q]; }
+  const int have = min(total, K);
+  for (int i = lane; i < bq_cnt[w]; i += 32)
+    if (start + i < K) o[start + i] = mine[i];
+  __syncthreads();                              // the first `have` outputs are in place (block-visible)
+  if (have == 0) {
+    for (int i = threadIdx.x; i < K; i += kBqSplit * 32) o[i] = 0;
+  } else if (have < K) {
+    for (int i = threadIdx.x; i < K - have; i += kBqSplit * 32) o[have + i] = o[i % have];
+  }
+}
+
 }  // namespace dib
 
 extern "C" {
@@ -202,9 +253,14 @@ int ball_query_forward(const float* dist, float radius, int32_t* out, int B, int
   const long long rows = (long long)B * M;
   if (rows == 0) return DIB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const long long blocks = (rows + kBqWarps - 1) / kBqWarps;
-  DIB_REQUIRE(blocks < (1ll << 31), "too many rows");
-  ball_query_kernel<<<(unsigned)blocks, kBqWarps * 32, 0, st>>>(dist, radius, out, rows, N, K);
+  const size_t split_smem = (size_t)kBqSplit * K * sizeof(int32_t);
+  if (split_smem <= 32 * 1024 && N >= 4096 && rows < (1ll << 31)) {
+    ball_query_split_kernel<<<(unsigned)rows, kBqSplit * 32, split_smem, st>>>(dist, radius, out, N, K);
+  } else {
+    const long long blocks = (rows + kBqWarps - 1) / kBqWarps;
+    DIB_REQUIRE(blocks < (1ll << 31), "too many rows");
+    ball_query_kernel<<<(unsigned)blocks, kBqWarps * 32, 0, st>>>(dist, radius, out, rows, N, K);
+  }
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }

@@ -92,6 +92,25 @@ def test_ball_query_adversarial(cuda):
     np.testing.assert_array_equal(got[0, 4, :6], [5, 17, 2000, 5, 17, 2000])
 
 
+def test_ball_query_split_path_adversarial(cuda):
+    """N >= 4096 takes the row-split kernel: hits only in a late quarter, exactly K hits spread over
+    the quarters, more than K in the first quarter, none, cyclic padding across quarter boundaries."""
+    B, M, N, K = 1, 8, 6000, 20
+    rng = np.random.default_rng(5)
+    dist = np.full((B, M, N), 5.0, dtype=np.float32)
+    radius = 1.0
+    dist[0, 0, [5990, 5995]] = 0.5                               # two hits at the very end -> cyclic repeat
+    dist[0, 1, :100] = 0.5                                        # > K hits in the first quarter
+    dist[0, 2, [10, 1600, 3100, 4600, 5999]] = 1.0                # one hit per quarter (+1), inclusive <=
+    dist[0, 3, rng.choice(N, K, replace=False)] = 0.0             # exactly K hits anywhere
+    dist[0, 4, rng.choice(N, 3 * K, replace=False)] = 0.0         # 3K hits anywhere
+    dist[0, 5, :] = np.nan
+    dist[0, 6, 1499:1503] = 0.1                                   # straddles the first quarter boundary (1504)
+    got = run_ball_query(dist, radius, K)
+    np.testing.assert_array_equal(got, oracle.ball_query(dist, radius, K))
+    np.testing.assert_array_equal(got[0, 0, :4], [5990, 5995, 5990, 5995])
+
+
 def test_golden_index_max(cuda):
     """Fixtures written by tests/golden/make_golden.py from the REFERENCE's own forward_cpu."""
     files = sorted(glob.glob(os.path.join(GOLDEN, "index_max_*.npz")))
