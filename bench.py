@@ -64,6 +64,20 @@ def load_measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(S_local, n_inits, is_2d):
+    """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed ncu --set full capture
+    (profiles/r01_traffic.json, written by scripts/ncu_traffic.py) -- only if it was taken on this workload."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if t["samples_per_gpu"] == S_local and t["inits"] == n_inits and bool(t["is_2d"]) == bool(is_2d):
+            return t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -371,7 +385,7 @@ def main():
             "mean_cloud_passes_per_solve": float(passes.mean().item()),
             "mean_lm_iterations_per_solve": float(stats[:, :, 0].mean().item()),
             "compulsory_bytes_per_launch": compulsory,
-            "traffic": None,
+            "traffic": load_traffic(S_local, n_inits, is_2d),
             "note": "algorithmic = 13 B x points x cloud passes the solver performed (streamed model, SURVEY 8d); the "
                     "cloud is re-read from L2/shared memory, so DRAM traffic (profiles/) is far below it",
         },

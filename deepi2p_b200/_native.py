@@ -16,6 +16,7 @@ EXPORTS = (
     "frustum_evaluate_workspace_bytes",
     "frustum_evaluate_f32", "frustum_evaluate_f64", "frustum_residuals_f32", "frustum_residuals_f64",
     "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32",
+    "frustum_inside_mask_f32", "pose_error_batch",
     "index_max_forward", "ball_query_forward",
 )
 
@@ -69,6 +70,10 @@ def load():
     lib.frustum_prepare_batch_f32.restype = i32
     lib.frustum_prepare_batch_f32.argtypes = [vp, vp, i32, i32, i32, i32, _c.c_uint64, f64, f64, i32,
                                               vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.frustum_inside_mask_f32.restype = i32
+    lib.frustum_inside_mask_f32.argtypes = [vp, vp, i32, vp, vp, f64, f64, i32, vp, vp]
+    lib.pose_error_batch.restype = i32
+    lib.pose_error_batch.argtypes = [vp, vp, i32, f64, f64, vp, vp, vp, vp]
     lib.index_max_forward.restype = i32
     lib.index_max_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
     lib.ball_query_forward.restype = i32

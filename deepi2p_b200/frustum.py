@@ -266,3 +266,49 @@ def solve_p_given_k(points, labels, K, init_y_angle, init_T, H, W, t_xyz_lower_b
               % (st[0], st[1], st[2], TERMINATION[st[3]] if 0 <= st[3] < len(TERMINATION) else st[3],
                  float(out["cost"][0])))
     return out["P"][0].cpu().numpy(), float(out["cost"][0].item()), res.cpu().numpy()
+
+
+def inside_mask_batch(xyz, n_pts, P, K, H, W, stream=None):
+    """Batched get_inside_img_mask (registration_lsq.py:67-84): int8 [S,Ns], 1 inside / 0 outside / -1 padding."""
+    _require_cuda()
+    lib = _native.load()
+    S, _, Ns = xyz.shape
+    dev = xyz.device
+    if xyz.dtype != torch.float32:
+        raise ValueError("inside_mask_batch takes float32 coordinates")
+    P16 = torch.as_tensor(P, dtype=torch.float64).to(dev).reshape(S, -1)
+    if P16.shape[1] == 12:
+        P16 = torch.cat([P16, torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float64, device=dev).expand(S, 4)], 1)
+    P16 = P16.contiguous()
+    K9 = _as_K(K, S, dev)
+    if n_pts is not None:
+        n_pts = n_pts.to(dev, torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        mask = torch.empty((S, Ns), dtype=torch.int8, device=dev)
+        rc = lib.frustum_inside_mask_f32(_ptr(xyz), _ptr(n_pts), Ns, _ptr(P16), _ptr(K9), float(H), float(W), S,
+                                         _ptr(mask), _stream_ptr(stream))
+    _native.check(rc, "frustum_inside_mask")
+    return mask
+
+
+def pose_error_batch(P_pred, P_gt, t_thresh=2.0, r_thresh=5.0, stream=None):
+    """Batched get_P_diff (registration_lsq.py:87-95) + the authors' success criterion
+    (registration_result_analysis.py:37-38).  Returns dict(t_err [S] m, r_err [S] deg, success [S] int32,
+    success_rate float tensor)."""
+    _require_cuda()
+    lib = _native.load()
+    Pp = torch.as_tensor(P_pred, dtype=torch.float64)
+    dev = Pp.device if Pp.is_cuda else torch.device("cuda")
+    Pp = Pp.to(dev).reshape(-1, 16).contiguous()
+    Pg = torch.as_tensor(P_gt, dtype=torch.float64).to(dev).reshape(-1, 16).contiguous()
+    S = Pp.shape[0]
+    if Pg.shape[0] != S:
+        raise ValueError("P_pred and P_gt must have the same batch size")
+    with torch.cuda.device(dev):
+        t_err = torch.empty((S,), dtype=torch.float64, device=dev)
+        r_err = torch.empty((S,), dtype=torch.float64, device=dev)
+        ok = torch.empty((S,), dtype=torch.int32, device=dev)
+        rc = lib.pose_error_batch(_ptr(Pp), _ptr(Pg), S, float(t_thresh), float(r_thresh), _ptr(t_err), _ptr(r_err),
+                                  _ptr(ok), _stream_ptr(stream))
+    _native.check(rc, "pose_error_batch")
+    return dict(t_err=t_err, r_err=r_err, success=ok, success_rate=ok.double().mean() if S else torch.tensor(0.0))

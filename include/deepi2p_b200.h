@@ -12,6 +12,8 @@
  *   frustum_residuals_*     the residual vector solvePGivenK returns  registration.cpp:150-155
  *   frustum_evaluate_*      (test hook: one cost/gradient/JtJ pass)   registration_{2d,3d}.hpp:34-68,105-127
  *   frustum_prepare_batch   get_initial_guess + init perturbation     evaluation/registration_lsq.py:196-220,163-164
+ *   frustum_inside_mask_f32 get_inside_img_mask                        evaluation/registration_lsq.py:67-84
+ *   pose_error_batch        get_P_diff + success criterion             evaluation/registration_lsq.py:87-95, registration_result_analysis.py:37-38
  *   index_max_forward       index_max.forward_cuda[_shared_mem]       models/index_max_ext/index_max_cuda.cu:30-62,84-100
  *   ball_query_forward      ball_query.forward_cuda_shared_mem        models/ball_query_ext/ball_query_cuda.cu:11-50,54-71
  *
@@ -125,6 +127,20 @@ int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in,
                               int8_t* label_out,
                               int32_t* n_pts, double* init, double* init_y_angle, int32_t* degenerate,
                               void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation-side ops.
+ *   frustum_inside_mask_f32: label rule of evaluation/registration_lsq.py:67-84 /
+ *       models/multimodal_classifier.py:136-148: mask[s][i] = 1 if 0<=u<=W-1, 0<=v<=H-1, z>0.1 for
+ *       [u v 1] ~ K (P p), else 0; -1 beyond n_pts[s].  P16 [S][16] row-major 4x4 (or 3x4 padded).
+ *   pose_error_batch: get_P_diff (registration_lsq.py:87-95) per sample: P_diff = P_pred^-1 P_gt,
+ *       t_err = |P_diff[:3,3]|, r_err_deg = sum |euler 'xzy'| in degrees; success (may be NULL) =
+ *       t_err < t_thresh_m and r_err_deg < r_thresh_deg (registration_result_analysis.py:37-38: 2 m, 5 deg).
+ * ------------------------------------------------------------------------------------------ */
+int frustum_inside_mask_f32(const float* xyz, const int32_t* n_pts, int n_stride, const double* P16,
+                            const double* K9, double H, double W, int S, int8_t* mask_out, dib_stream_t stream);
+int pose_error_batch(const double* P_pred16, const double* P_gt16, int S, double t_thresh_m, double r_thresh_deg,
+                     double* t_err, double* r_err_deg, int32_t* success, dib_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Segmented arg-max (index_max) and first-K-in-radius (ball_query).  Bit-exact index outputs.

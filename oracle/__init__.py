@@ -173,6 +173,31 @@ def solve_multistart(points, labels, K, init_ry, init_t, H, W, t_lb, t_ub, max_i
                 poses=np.stack([o[0] for o in outs]))
 
 
+def inside_img_mask(pc, P, K, H, W):
+    """get_inside_img_mask (evaluation/registration_lsq.py:67-84), restated line by line."""
+    pc = np.asarray(pc, dtype=np.float64)
+    P = np.asarray(P, dtype=np.float64)
+    K = np.asarray(K, dtype=np.float64)
+    homo = np.concatenate((pc, np.ones((1, pc.shape[1]), dtype=pc.dtype)), axis=0)
+    P_points = np.dot(P, homo)[0:3, :]
+    K_pc = np.dot(K, P_points)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        pxpy = K_pc[0:2, :] / K_pc[2:3, :]
+    x_in = np.logical_and(pxpy[0:1, :] >= 0, pxpy[0:1, :] <= W - 1)
+    y_in = np.logical_and(pxpy[1:2, :] >= 0, pxpy[1:2, :] <= H - 1)
+    z_in = P_points[2:3, :] > 0.1
+    return np.logical_and(np.logical_and(x_in, y_in), z_in)[0]
+
+
+def pose_diff(P_pred, P_gt):
+    """get_P_diff (evaluation/registration_lsq.py:87-95): (t_diff, angles_diff in degrees)."""
+    from scipy.spatial.transform import Rotation
+    P_diff = np.dot(np.linalg.inv(P_pred), P_gt)
+    t_diff = np.linalg.norm(P_diff[0:3, 3])
+    angles = np.sum(np.abs(Rotation.from_matrix(P_diff[0:3, 0:3]).as_euler('xzy', degrees=True)))
+    return t_diff, angles
+
+
 def index_max(data, index, K):
     """Oracle for index_max.forward_* (index_max.cpp:73-112)."""
     lib = _lib("libops_oracle.so")

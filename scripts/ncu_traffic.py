@@ -1,0 +1,19 @@
+#!/usr/bin/env python
+"""Extract DRAM traffic of the solve kernel from an ncu report into profiles/r01_traffic.json.
+   python scripts/ncu_traffic.py gpurun_out/prof_X_solve.ncu-rep <samples_per_gpu> <inits> <is_2d 0|1>"""
+import csv, io, json, os, subprocess, sys
+rep, S, I, is2d = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(raw)))
+hdr, units, vals = rows[0], rows[1], rows[2]
+def get(name):
+    i = hdr.index(name); v = float(vals[i].replace(",", "")); u = units[i]
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
+out = {"kernel": vals[hdr.index("Kernel Name")], "samples_per_gpu": S, "inits": I, "is_2d": bool(is2d),
+       "dram_bytes_read": get("dram__bytes_read.sum"), "dram_bytes_write": get("dram__bytes_write.sum"),
+       "lts_t_bytes": get("lts__t_bytes.sum") if "lts__t_bytes.sum" in hdr else None,
+       "gpu_time_ns": float(vals[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}[units[hdr.index("gpu__time_duration.sum")]],
+       "source": os.path.basename(rep)}
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+json.dump(out, open(os.path.join(root, "profiles", "r01_traffic.json"), "w"), indent=1)
+print(out)

@@ -12,7 +12,7 @@ python bench.py --is-3d --steps 3 --warmup 3 --no-cpu-baseline --samples-per-gpu
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:frustum_solve -s 1 -c 1 -o gpurun_out/prof_${tag}_solve \
-    python bench.py --samples-per-gpu 128 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_solve_${tag}.log 2>&1
+    python bench.py --samples-per-gpu 512 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_solve_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:index_max_kernel\|ball_query_kernel -s 8 -c 2 -o gpurun_out/prof_${tag}_ops \
     python bench.py --ops-only > gpurun_out/ncu_ops_${tag}.log 2>&1
 python - <<PY

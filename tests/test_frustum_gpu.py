@@ -393,3 +393,38 @@ def test_large_cloud_unsorted_fallback_and_oxford_6dof(cuda):
             c_at = oracle.evaluate(pf, lf, smp["K"], p[:P], smp["H"], smp["W"], is_2d)[0]
             assert abs(out["costs"][0, i].item() - c_at) <= 1e-9 * max(1.0, c_at)
         assert ok >= 2
+
+
+def test_inside_mask_and_pose_error_ops(cuda):
+    """N3 ops: label projection rule and the RTE/RRE metric, vs line-by-line restatements of the reference's
+    numpy/scipy code (oracle.inside_img_mask / oracle.pose_diff)."""
+    from scipy.spatial.transform import Rotation
+    S, n = 5, 3000
+    smps = [small_sample(500 + s, n) for s in range(S)]
+    xyz, _, n_pts = frustum.pack_clouds(np.stack([s["points"] for s in smps]), np.stack([s["pred"] for s in smps]),
+                                        n_pts=np.array([n, n, 2000, 17, 0], dtype=np.int32))
+    P = np.stack([s["P_gt"] for s in smps])
+    mask = frustum.inside_mask_batch(xyz, n_pts, P, smps[0]["K"], smps[0]["H"], smps[0]["W"]).cpu().numpy()
+    for s, m in enumerate([n, n, 2000, 17, 0]):
+        want = oracle.inside_img_mask(smps[s]["points"][:, :m], P[s], smps[s]["K"], smps[s]["H"], smps[s]["W"])
+        np.testing.assert_array_equal(mask[s, :m], want.astype(np.int8))
+        assert (mask[s, m:] == -1).all()
+        if m == n:
+            np.testing.assert_array_equal(mask[s, :n], smps[s]["gt"].astype(np.int8))   # the generator's own labels
+    # pose errors
+    rng = np.random.default_rng(0)
+    Pp, Pg = [], []
+    for i in range(64):
+        A = np.eye(4); B = np.eye(4)
+        A[:3, :3] = Rotation.from_euler("yxz", rng.uniform(-3, 3, 3)).as_matrix(); A[:3, 3] = rng.uniform(-10, 10, 3)
+        d = Rotation.from_euler("xzy", rng.normal(0, 0.05 if i % 2 else 0.5, 3)).as_matrix()
+        B[:3, :3] = A[:3, :3] @ d; B[:3, 3] = A[:3, 3] + rng.normal(0, 1.0 if i % 2 else 3.0, 3)
+        Pp.append(A); Pg.append(B)
+    out = frustum.pose_error_batch(np.stack(Pp), np.stack(Pg))
+    te, re, ok = out["t_err"].cpu().numpy(), out["r_err"].cpu().numpy(), out["success"].cpu().numpy()
+    for i in range(64):
+        t_want, r_want = oracle.pose_diff(Pp[i], Pg[i])
+        assert abs(te[i] - t_want) < 1e-9 and abs(re[i] - r_want) < 1e-7, (i, te[i], t_want, re[i], r_want)
+        assert ok[i] == int(t_want < 2 and r_want < 5)
+    assert abs(out["success_rate"].item() - ok.mean()) < 1e-12
+    assert 0 < ok.sum() < 64
