@@ -17,7 +17,7 @@ EXPORTS = (
     "frustum_evaluate_f32", "frustum_evaluate_f64", "frustum_residuals_f32", "frustum_residuals_f64",
     "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32",
     "frustum_inside_mask_f32", "pose_error_batch",
-    "index_max_forward", "ball_query_forward",
+    "index_max_forward", "ball_query_forward", "ball_query_xyz_workspace_bytes", "ball_query_xyz_forward",
 )
 
 
@@ -76,6 +76,10 @@ def load():
     lib.pose_error_batch.argtypes = [vp, vp, i32, f64, f64, vp, vp, vp, vp]
     lib.index_max_forward.restype = i32
     lib.index_max_forward.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.ball_query_xyz_workspace_bytes.restype = sz
+    lib.ball_query_xyz_workspace_bytes.argtypes = [i32, i32]
+    lib.ball_query_xyz_forward.restype = i32
+    lib.ball_query_xyz_forward.argtypes = [vp, vp, _c.c_float, vp, i32, i32, i32, i32, vp, sz, vp]
     lib.ball_query_forward.restype = i32
     lib.ball_query_forward.argtypes = [vp, _c.c_float, vp, i32, i32, i32, i32, vp]
     _lib = lib

@@ -55,3 +55,32 @@ def ball_query_forward(node_to_point_dist, radius, K):
                                     torch.cuda.current_stream().cuda_stream)
     _native.check(rc, "ball_query_forward")
     return out
+
+
+_xyz_ws = {}
+
+
+def ball_query_xyz_forward(points, nodes, radius, K):
+    """Grid-hash radius search from coordinates: points [B,3,N], nodes [B,3,M] float32 CUDA -> int32 [B,M,K]
+    with the ball_query contract (first K indices in ascending n within radius; none -> 0; fewer -> cyclic).
+    Equivalent to ball_query_forward on the float32 distance matrix, without ever building it."""
+    _check_input(points, "points", torch.float32)
+    _check_input(nodes, "nodes", torch.float32)
+    if points.dim() != 3 or nodes.dim() != 3 or points.shape[1] != 3 or nodes.shape[1] != 3 or points.shape[0] != nodes.shape[0]:
+        raise RuntimeError("points must be [B,3,N] and nodes [B,3,M]")
+    lib = _native.load()
+    B, _, N = points.shape
+    M = nodes.shape[2]
+    K = int(K)
+    dev = points.device
+    with torch.cuda.device(dev):
+        need = lib.ball_query_xyz_workspace_bytes(B, N)
+        ws = _xyz_ws.get(dev.index)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
+            _xyz_ws[dev.index] = ws
+        out = torch.empty((B, M, K), dtype=torch.int32, device=dev)
+        rc = lib.ball_query_xyz_forward(points.data_ptr(), nodes.data_ptr(), float(radius), out.data_ptr(), B, M, N, K,
+                                        ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "ball_query_xyz_forward")
+    return out

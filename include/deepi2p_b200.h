@@ -152,6 +152,15 @@ int index_max_forward(const float* data, const int32_t* index, int32_t* out,
 int ball_query_forward(const float* dist, float radius, int32_t* out,
                        int B, int M, int N, int K, dib_stream_t stream);
 
+/* Coordinate-based variant: same output contract as ball_query_forward, computed with a
+ * uniform grid hash from  points [B][3][N] f32  and  nodes [B][3][M] f32  (channel-first, as
+ * models/networks_pc.py:47-65 holds them) -- the dense B x M x N distance matrix is never built.
+ * hit <=> ((dx*dx + dy*dy) + dz*dz) <= radius*radius in float32 without fma.  N <= 65536.
+ * workspace: [dev], 16-byte aligned, >= ball_query_xyz_workspace_bytes(B, N). */
+size_t ball_query_xyz_workspace_bytes(int B, int N);
+int ball_query_xyz_forward(const float* points, const float* nodes, float radius, int32_t* out, int B, int M, int N,
+                           int K, void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

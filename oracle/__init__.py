@@ -223,3 +223,21 @@ def ball_query(dist, radius, K):
     lib.ball_query_oracle(_p(dist, ctypes.c_float), ctypes.c_float(float(radius)), _p(out, ctypes.c_int32),
                           ctypes.c_int64(B), ctypes.c_int64(M), ctypes.c_int64(N), ctypes.c_int64(K))
     return out
+
+
+def ball_query_xyz(points, nodes, radius, K):
+    """Oracle for the coordinate-based radius search: float32 distance ((dx*dx + dy*dy) + dz*dz) <= r*r, then
+    the ball_query rule (ball_query_cuda.cu:11-50).  points [B,3,N], nodes [B,3,M]."""
+    p = np.asarray(points, dtype=np.float32)
+    q = np.asarray(nodes, dtype=np.float32)
+    d = p[:, :, None, :] - q[:, :, :, None]                     # [B,3,M,N], point - node as in the kernel
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    r2 = np.float32(radius) * np.float32(radius)
+    B, M, N = d2.shape
+    out = np.zeros((B, M, K), dtype=np.int32)
+    for b in range(B):
+        for m in range(M):
+            hits = np.nonzero(d2[b, m] <= r2)[0][:K]
+            if len(hits):
+                out[b, m] = [hits[i] if i < len(hits) else hits[(i - len(hits)) % len(hits)] for i in range(K)]
+    return out

@@ -159,3 +159,26 @@ def test_argument_checks(cuda):
         point_ops.index_max_forward(d.transpose(1, 2), torch.zeros(2, 2, dtype=torch.int32, device="cuda"), 2)
     with pytest.raises(RuntimeError):
         point_ops.ball_query_forward(torch.zeros(1, 1, 4), 1.0, 2)
+
+
+@pytest.mark.parametrize("B,M,N,K,cube,radius", [(2, 16, 4096, 32, 20.0, 2.0), (1, 64, 16384, 64, 20.0, 2.0),
+                                                 (2, 8, 1000, 16, 5.0, 30.0), (1, 4, 50, 8, 1.0, 0.05),
+                                                 (1, 5, 3000, 10, 0.0, 1.0)])
+def test_ball_query_xyz_grid_hash(cuda, B, M, N, K, cube, radius):
+    """Grid-hash radius search == the float32 restatement (and hence == ball_query on the same distances)."""
+    rng = np.random.default_rng(N + K)
+    pts = rng.uniform(0, cube, (B, 3, N)).astype(np.float32) if cube > 0 else np.zeros((B, 3, N), np.float32)
+    nodes = rng.uniform(-0.1 * cube, 1.1 * cube, (B, 3, M)).astype(np.float32) if cube > 0 else np.zeros((B, 3, M), np.float32)
+    if cube > 0:
+        nodes[:, :, 0] = pts[:, :, 7]                    # a node exactly on a point (d = 0)
+        nodes[0, :, 1] = [1e6, 1e6, 1e6]                 # far outside the bounding box: no hits -> zeros
+    got = point_ops.ball_query_xyz_forward(torch.from_numpy(pts).cuda(), torch.from_numpy(nodes).cuda(), radius, K).cpu().numpy()
+    want = oracle.ball_query_xyz(pts, nodes, radius, K)
+    np.testing.assert_array_equal(got, want)
+    if cube > 0:
+        assert (got[0, 1] == 0).all()
+    # consistency with the dense op on the same float32 squared distances (compare d2 <= r2 via sqrt-free matrix)
+    d = pts[:, :, None, :] - nodes[:, :, :, None]
+    d2 = ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(np.float32)
+    dense = run_ball_query(d2, float(np.float32(radius) * np.float32(radius)), K)
+    np.testing.assert_array_equal(got, dense)
