@@ -375,7 +375,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "registrations/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h,
                 "note": "pinned host xyz f32 + pred int8 -> device, register_batch, poses+cost -> pinned host"},
-        "gpu_launches": 3 * args.steps,
+        "gpu_launches": 5 * args.steps,   # prepare, boxes, order, solve, finalize per step
         "clocks": clocks,
         "roofline": {
             "bound": "hbm", "kernel": "frustum_solve_kernel<float,%d>" % (4 if is_2d else 6),
