@@ -332,8 +332,9 @@ def main():
 
     # ---- roofline of the dominant kernel: the solve launch alone, CUDA events on its stream
     prep = frustum.prepare_batch(xyz_d, pred_d, n_points, n_inits, seed=12345)
-    frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500, is_2d=is_2d)
-    k_ms = 0.0
+    res = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500,
+                              is_2d=is_2d, return_all=True)       # warm-up; its buffers are reused below (no allocation
+    k_ms = 0.0                                                     # inside the timed region)
     k_all = []
     reps = max(3, min(args.steps, 5))
     for _ in range(reps):
@@ -342,7 +343,7 @@ def main():
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
         res = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500,
-                                  is_2d=is_2d, return_all=True)
+                                  is_2d=is_2d, return_all=True, out=res)
         e1.record(); e1.synchronize()
         k_all.append(e0.elapsed_time(e1))
     k_ms = sum(k_all) / reps

@@ -96,13 +96,15 @@ def _workspace(nbytes, device):
 
 
 def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB, max_iter=500,
-                is_2d=True, return_all=False, stream=None):
+                is_2d=True, return_all=False, stream=None, out=None):
     """Batched multi-start solve, everything resident on the device.
 
     xyz [S,3,Ns] f32|f64 cuda, label [S,Ns] int8 cuda, n_pts [S] int32 cuda or None,
     K [S,9]|[9]|[3,3] f64, init [S,I,4] f64 = (init_y_angle, Tx, Ty, Tz) per problem.
     Returns dict(P [S,4,4], cost [S], best [S]) (+ params [S,I,6], costs [S,I], stats [S,I,4]
     = (LM iterations, cloud passes, line-search contractions, termination) if return_all).
+    `out`: a dict returned by an earlier call with the same shapes; its tensors are overwritten in place
+    (no allocation inside the call).
     """
     _require_cuda()
     lib = _native.load()
@@ -126,14 +128,23 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
     lb = np.ascontiguousarray(np.asarray(t_lb, dtype=np.float64).reshape(3))
     ub = np.ascontiguousarray(np.asarray(t_ub, dtype=np.float64).reshape(3))
     with torch.cuda.device(dev):
-        P = torch.empty((S, 4, 4), dtype=torch.float64, device=dev)
-        cost = torch.empty((S,), dtype=torch.float64, device=dev)
-        best = torch.empty((S,), dtype=torch.int32, device=dev)
         params = costs = stats = None
-        if return_all:
-            params = torch.empty((S, I, 6), dtype=torch.float64, device=dev)
-            costs = torch.empty((S, I), dtype=torch.float64, device=dev)
-            stats = torch.empty((S, I, 4), dtype=torch.int32, device=dev)
+        if out is not None:
+            P, cost, best = out["P"], out["cost"], out["best"]
+            if tuple(P.shape) != (S, 4, 4) or P.device != dev:
+                raise ValueError("out buffers do not match this batch")
+            if return_all:
+                params, costs, stats = out["params"], out["costs"], out["stats"]
+                if tuple(params.shape) != (S, I, 6):
+                    raise ValueError("out buffers do not match this batch")
+        else:
+            P = torch.empty((S, 4, 4), dtype=torch.float64, device=dev)
+            cost = torch.empty((S,), dtype=torch.float64, device=dev)
+            best = torch.empty((S,), dtype=torch.int32, device=dev)
+            if return_all:
+                params = torch.empty((S, I, 6), dtype=torch.float64, device=dev)
+                costs = torch.empty((S, I), dtype=torch.float64, device=dev)
+                stats = torch.empty((S, I, 4), dtype=torch.int32, device=dev)
         wsb = lib.frustum_solve_workspace_bytes(S, I, Ns)
         ws = _workspace(wsb, dev)
         fn = lib.frustum_solve_batch_f32 if xyz.dtype == torch.float32 else lib.frustum_solve_batch_f64
@@ -141,10 +152,10 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
                 float(H), float(W), int(max_iter), 1 if is_2d else 0, S, I, _ptr(P), _ptr(cost), _ptr(best),
                 _ptr(params), _ptr(costs), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(stream))
     _native.check(rc, "frustum_solve_batch")
-    out = dict(P=P, cost=cost, best=best)
+    res = dict(P=P, cost=cost, best=best)
     if return_all:
-        out.update(params=params, costs=costs, stats=stats)
-    return out
+        res.update(params=params, costs=costs, stats=stats)
+    return res
 
 
 def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None):
