@@ -482,6 +482,12 @@ constexpr int kBoxRoundFloats = kBoxFields * kThreads;
 #ifndef DIB_BOX_ROUNDS
 #define DIB_BOX_ROUNDS 8
 #endif
+#ifndef DIB_GROUP_TMA
+#define DIB_GROUP_TMA 0                       // 1: undecided groups are staged by cp.async.bulk (TMA engine) into a per-warp
+#endif                                        //    double buffer one step ahead; 0: plain coalesced loads into registers.
+                                              //    Measured on B200, same call (profiles/r01_sweep_build_params.jsonl):
+                                              //    TMA 133 ms vs loads 103 ms per 512x60 problems -- 128-byte bulk copies
+                                              //    cost more than the 8 coalesced loads they replace.
 #ifndef DIB_GPS
 #define DIB_GPS 2                             // undecided groups fetched + classified per step
 #endif
@@ -585,10 +591,21 @@ constexpr int kBatch = 32 * DIB_EXACT_ILP;   // entries evaluated per exact-path
 constexpr int kRing = 256;               // pending ring per label: < kBatch carried + at most DIB_GPS x 32 appended per step
 static_assert(kBatch + 32 * DIB_GPS <= kRing, "ring too small");
 
+// Per-warp staging buffer of one step's undecided groups (filled by bulk copies).
+template <typename CT>
+struct alignas(16) GroupStage {
+  CT x[DIB_GPS][32];
+  CT y[DIB_GPS][32];
+  CT z[DIB_GPS][32];
+  int8_t lab[DIB_GPS][32];
+};
+
 template <typename CT, int P>
 struct Smem {
   alignas(16) float box[kBoxRounds][kBoxRoundFloats];   // bulk-copied (TMA engine) once per problem
   Entry<CT> list[kWarps][2][kRing];                     // [label 0 | label 1] pending rings
+  GroupStage<CT> gstage[kWarps][2];                     // double-buffered group staging, private to each warp
+  alignas(8) uint64_t gbar[kWarps][2];                  // their mbarriers
   alignas(8) uint64_t full;                             // mbarrier of the box-table copy
   double red[kWarps][NAcc<P>::N];
   double tot[NAcc<P>::N];
@@ -643,7 +660,7 @@ __device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst&
 // ------------------------------------------------------------------------------------------
 template <typename CT, int P>
 __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, int n_stride, int n,
-                               const float* box_s, bool boxes_resident, uint32_t& box_phase) {
+                               const float* box_s, bool boxes_resident, uint32_t& box_phase, uint32_t& gphase) {
   constexpr int N = NAcc<P>::N;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -696,6 +713,139 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
 #endif
       mask = __ballot_sync(0xffffffffu, box_undecided(box_cur, cc));
     }
+#if DIB_GROUP_TMA
+    // Undecided groups are taken DIB_GPS at a time and STAGED BY THE TMA ENGINE: lane 0 issues one
+    // cp.async.bulk per coordinate array and group (128 B of x, y, z and 32 B of labels) into this warp's
+    // double buffer, one step ahead of its use, completion signalled on the slot's mbarrier.  While the
+    // copies fly the warp drains pending exact-path batches; then it classifies the staged groups
+    // (independent instruction streams) and appends.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
+    int cur_cnt = 0, cur_g[DIB_GPS], slot = 0;
+    auto take_and_issue = [&](int which, int* g_out) -> int {
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < DIB_GPS; ++u) {
+        g_out[u] = -1;
+        if (mask) {
+          const int b = __ffs(mask) - 1;
+          mask &= mask - 1;
+          g_out[u] = r * kThreads + b * kWarps + warp;
+          ++cnt;
+        }
+      }
+      if (cnt && lane == 0) {
+        GroupStage<CT>& gs = sm.gstage[warp][which];
+        uint64_t* bar = &sm.gbar[warp][which];
+        uint32_t bytes = 0;
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u)
+          if (g_out[u] >= 0) {
+            int c = n_stride - g_out[u] * 32;           // points of this group inside the row (multiple of 16)
+            c = c > 32 ? 32 : c;
+            bytes += (uint32_t)c * (3u * sizeof(CT) + 1u);
+          }
+        mbar_expect_tx(bar, bytes);
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u)
+          if (g_out[u] >= 0) {
+            const int base = g_out[u] * 32;
+            int c = n_stride - base;
+            c = c > 32 ? 32 : c;
+            bulk_g2s(gs.x[u], xyz_s + base, (uint32_t)c * sizeof(CT), bar);
+            bulk_g2s(gs.y[u], xyz_s + n_stride + base, (uint32_t)c * sizeof(CT), bar);
+            bulk_g2s(gs.z[u], xyz_s + 2 * (size_t)n_stride + base, (uint32_t)c * sizeof(CT), bar);
+            bulk_g2s(gs.lab[u], lab_s + base, (uint32_t)c, bar);
+          }
+      }
+      return cnt;
+    };
+    if (mask) cur_cnt = take_and_issue(slot, cur_g);
+#pragma unroll 1
+    do {
+      int nxt_cnt = 0, nxt_g[DIB_GPS];
+#pragma unroll
+      for (int u = 0; u < DIB_GPS; ++u) nxt_g[u] = -1;
+      if (mask) nxt_cnt = take_and_issue(slot ^ 1, nxt_g);
+#pragma unroll 1
+      while (pend0 >= threshold) {
+        __syncwarp();
+        const int take = pend0 < kBatch ? pend0 : kBatch;
+        const Entry<CT> ea = ring0[(head0 + lane) & (kRing - 1)];
+        Out0<P> oa;
+        eval_outside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
+#if DIB_EXACT_ILP == 2
+        const Entry<CT> eb = ring0[(head0 + 32 + lane) & (kRing - 1)];
+        Out0<P> ob;
+        eval_outside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
+        prod *= oa.s1 * ob.s1;
+#else
+        prod *= oa.s1;
+#endif
+        renorm_product(prod, expo);
+        rank1<P>(acc, oa.J, oa.w, oa.r);
+#if DIB_EXACT_ILP == 2
+        rank1<P>(acc, ob.J, ob.w, ob.r);
+#endif
+        head0 = (head0 + take) & (kRing - 1);
+        pend0 -= take;
+      }
+#pragma unroll 1
+      while (pend1 >= threshold) {
+        __syncwarp();
+        const int take = pend1 < kBatch ? pend1 : kBatch;
+        const Entry<CT> ea = ring1[(head1 + lane) & (kRing - 1)];
+        Out1<P> oa;
+        eval_inside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
+#if DIB_EXACT_ILP == 2
+        const Entry<CT> eb = ring1[(head1 + 32 + lane) & (kRing - 1)];
+        Out1<P> ob;
+        eval_inside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
+        prod *= oa.s1 * ob.s1;
+#else
+        prod *= oa.s1;
+#endif
+        renorm_product(prod, expo);
+        accumulate_inside<P>(acc, oa);
+#if DIB_EXACT_ILP == 2
+        accumulate_inside<P>(acc, ob);
+#endif
+        head1 = (head1 + take) & (kRing - 1);
+        pend1 -= take;
+      }
+      if (cur_cnt) {
+        mbar_wait(&sm.gbar[warp][slot], (gphase >> slot) & 1u);
+        gphase ^= 1u << slot;
+        const GroupStage<CT>& gs = sm.gstage[warp][slot];
+        CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+        int glab[DIB_GPS];
+        bool mb[DIB_GPS];
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) {
+          const bool in = cur_g[u] >= 0 && cur_g[u] * 32 + lane < n;
+          gx[u] = in ? gs.x[u][lane] : (CT)0; gy[u] = in ? gs.y[u][lane] : (CT)0; gz[u] = in ? gs.z[u][lane] : (CT)0;
+          glab[u] = in ? (int)gs.lab[u][lane] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) {
+          const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
+          const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
+          if (mb[u]) {
+            Entry<CT> e;
+            e.x = gx[u]; e.y = gy[u]; e.z = gz[u]; e.lab = glab[u];
+            if (glab[u]) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
+            else         ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
+          }
+          pend0 += __popc(m0);
+          pend1 += __popc(m1);
+        }
+      }
+      cur_cnt = nxt_cnt;
+#pragma unroll
+      for (int u = 0; u < DIB_GPS; ++u) cur_g[u] = nxt_g[u];
+      slot ^= 1;
+    } while (cur_cnt);
+#else
     // Undecided groups are taken DIB_GPS at a time.  Their loads are issued first, then the pending
     // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
     // (independent instruction streams) and appended.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
@@ -784,6 +934,7 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         }
             }
     } while (mask);
+#endif
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
@@ -1343,10 +1494,11 @@ __global__ void __launch_bounds__(kThreads, (P == 4) ? DIB_MINBLOCKS4 : DIB_MINB
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&sm.full, 1);
+    for (int w = 0; w < kWarps; ++w) { mbar_init(&sm.gbar[w][0], 1); mbar_init(&sm.gbar[w][1], 1); }
     mbar_fence_init();
   }
   __syncthreads();
-  uint32_t box_phase = 0;
+  uint32_t box_phase = 0, gphase = 0;      // gphase: bit s = parity of this warp's staging slot s
   const int total = a.S * a.I;
 
   for (;;) {
@@ -1380,7 +1532,7 @@ __global__ void __launch_bounds__(kThreads, (P == 4) ? DIB_MINBLOCKS4 : DIB_MINB
     const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);   // overlaps thread 0's set-up
     __syncthreads();
     while (sm.go == LM_EVAL) {
-      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, a.n_stride, n, box_s, resident, box_phase);
+      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, a.n_stride, n, box_s, resident, box_phase, gphase);
       if (tid == 0) {
         const int rc = lm_consume<P>(sm.lm, sm.tot);
         sm.go = rc;
@@ -1455,19 +1607,20 @@ __global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xy
   const int s = blockIdx.x;
   if (tid == 0) {
     mbar_init(&sm.full, 1);
+    for (int w = 0; w < kWarps; ++w) { mbar_init(&sm.gbar[w][0], 1); mbar_init(&sm.gbar[w][1], 1); }
     mbar_fence_init();
     make_cam(K9 + (size_t)s * 9, H, W, &sm.cam);
     make_pose<P>(x + (size_t)s * 6, &sm.pose);
     make_class(sm.pose, sm.cam, &sm.cls);
   }
   __syncthreads();
-  uint32_t box_phase = 0;
+  uint32_t box_phase = 0, gphase = 0;
   const int n = n_pts ? n_pts[s] : n_stride;
   const float* box_s = boxes + (size_t)s * rounds_max * kBoxRoundFloats;
   const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);
   __syncthreads();
   evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride, n_stride, n, box_s, resident,
-                        box_phase);
+                        box_phase, gphase);
   if (tid == 0) {
     cost_out[s] = sm.tot[0];
     for (int j = 0; j < 6; ++j) grad_out[(size_t)s * 6 + j] = (j < P) ? sm.tot[1 + j] : 0.0;
