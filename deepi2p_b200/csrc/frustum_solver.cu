@@ -458,9 +458,11 @@ __device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab,
   }
   const float bl = fmaf(cc.bl[0], x, fmaf(cc.bl[1], y, fmaf(cc.bl[2], z, cc.bl[3])));
   const float bh = fmaf(cc.bh[0], x, fmaf(cc.bh[1], y, fmaf(cc.bh[2], z, cc.bh[3])));
+  // al > m, ah < -m, bl > m, bh < -m  <=>  lo4 > m ;   al < -m or ah > m or bl < -m or bh > m  <=>  lo4 < -m
+  const float lo4 = fminf(fminf(al, -ah), fminf(bl, -bh));
   const bool front = Z > m;
-  const bool inside = front && al > m && ah < -m && bl > m && bh < -m;                       // surely in the image
-  const bool outside = (Z < -m) || (front && (al < -m || ah > m || bl < -m || bh > m));      // surely not
+  const bool inside = front && lo4 > m;                    // surely in the image
+  const bool outside = (Z < -m) || (front && lo4 < -m);    // surely not
   return lab == 1 ? !inside : !outside;
 }
 
@@ -645,8 +647,8 @@ __device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst&
     lo[k] = mid - rad; hi[k] = mid + rad;
   }
   const bool front = lo[0] > m;
-  const bool all_out = (hi[0] < -m) || (front && (hi[1] < -m || lo[2] > m || hi[3] < -m || lo[4] > m));
-  const bool all_in = front && lo[1] > m && hi[2] < -m && lo[3] > m && hi[4] < -m;
+  const bool all_out = (hi[0] < -m) || (front && fminf(fminf(hi[1], -lo[2]), fminf(hi[3], -lo[4])) < -m);
+  const bool all_in = front && fminf(fminf(lo[1], -hi[2]), fminf(lo[3], -hi[4])) > m;
   const bool skip = (!(flags & 1) || all_out) && (!(flags & 2) || all_in);
   return !skip;
 }
