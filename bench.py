@@ -457,7 +457,7 @@ def bench_ops(torch, dev, peak):
         pts = torch.rand((B, N, 3), device=dev, generator=g) * 20
         nodes = torch.rand((B, C, 3), device=dev, generator=g) * 20
         dist_m = torch.cdist(nodes, pts).contiguous()
-        sets.append((data, index, dist_m))
+        sets.append((data, index, dist_m, pts.transpose(1, 2).contiguous(), nodes.transpose(1, 2).contiguous()))
         del pts, nodes
     radius = float(torch.kthvalue(sets[0][2], K, dim=2).values.median().item())
 
@@ -480,10 +480,11 @@ def bench_ops(torch, dev, peak):
 
     im_ms = t(lambda i: point_ops.index_max_forward(sets[i][0], sets[i][1], K))
     bq_ms = t(lambda i: point_ops.ball_query_forward(sets[i][2], radius, K))
+    xyz_ms = t(lambda i: point_ops.ball_query_xyz_forward(sets[i][3], sets[i][4], radius, K))
     im_bytes = 4 * B * C * N + 4 * B * N + 4 * B * C * K
     # algorithmic bytes of ball_query: up to each row's K-th hit (mean over the two sets)
     bq_bytes = 0.0
-    for _, _, dist_m in sets:
+    for _, _, dist_m, _, _ in sets:
         csum = (dist_m <= radius).cumsum(2)
         kth = torch.where(csum[:, :, -1] >= K, (csum >= K).float().argmax(2) + 1, torch.full_like(csum[:, :, -1], N))
         bq_bytes += 0.5 * (float(kth.sum().item()) * 4 + 4 * B * C * K)
@@ -494,6 +495,9 @@ def bench_ops(torch, dev, peak):
         "ball_query": {"us": bq_ms * 1e3, "GBps_algorithmic": bq_bytes / (bq_ms * 1e-3) / 1e9,
                        "frac_algorithmic": bq_bytes / (bq_ms * 1e-3) / 1e9 / peak, "bytes_algorithmic": bq_bytes,
                        "bytes_upper_bound": 4 * B * C * N + 4 * B * C * K, "radius": radius},
+        "ball_query_xyz": {"us": xyz_ms * 1e3, "note": "grid-hash radius search from coordinates (grid build + query); reads "
+                           "%.1f MB instead of the %.0f MB distance matrix the dense op needs" % (
+                               (12 * B * N + 12 * B * C) / 1e6, 4 * B * C * N / 1e6)},
         "shape": {"B": B, "C": C, "M": C, "N": N, "K": K},
         "l2": "two alternating 268 MB input sets per op (> L2), no flush; 10 back-to-back launches per event pair",
     }
