@@ -128,8 +128,14 @@ __device__ __noinline__ void make_pose(const double* x, PoseConst* pc) {
 // Per-point evaluation.  acc = [cost, g[P], packed upper J^T J]; everything weighted by the
 // Cauchy corrector w = rho'(s) = 1/(1+s) (CauchyLoss(1.0), registration.cpp:103,121).
 // ------------------------------------------------------------------------------------------
-template <int P>
-__device__ __forceinline__ void rank1(double* acc, const double* J, double w, double r) {
+// Accumulator view over shared memory: acc[j] is column `lane` of row j ([N][32] doubles per warp).
+struct SmemAcc {
+  double* base;
+  __device__ __forceinline__ double& operator[](int j) const { return base[j * 32]; }
+};
+
+template <int P, typename ACC>
+__device__ __forceinline__ void rank1(ACC acc, const double* J, double w, double r) {
   const double wr = w * r;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
@@ -231,16 +237,16 @@ __device__ __forceinline__ void point_accumulate(double px, double py, double pz
     const double sum = 1.0 + s;
     const double w = 1.0 / sum;
     acc[0] += 0.5 * log(sum);
-    rank1<P>(acc, J[0], w, r[0]);
+    rank1<P, double*>(acc, J[0], w, r[0]);
   } else {
     const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
     const double sum = 1.0 + s;
     const double w = 1.0 / sum;
     acc[0] += 0.5 * log(sum);
     // rows with a zero selector are exactly zero and contribute nothing
-    if (r[0] != 0.0 || J[0][P - 3] != 0.0) rank1<P>(acc, J[0], w, r[0]);
-    if (r[1] != 0.0 || J[1][P - 2] != 0.0) rank1<P>(acc, J[1], w, r[1]);
-    if (J[2][P - 1] != 0.0) rank1<P>(acc, J[2], w, r[2]);
+    if (r[0] != 0.0 || J[0][P - 3] != 0.0) rank1<P, double*>(acc, J[0], w, r[0]);
+    if (r[1] != 0.0 || J[1][P - 2] != 0.0) rank1<P, double*>(acc, J[1], w, r[1]);
+    if (J[2][P - 1] != 0.0) rank1<P, double*>(acc, J[2], w, r[2]);
   }
 }
 
@@ -354,8 +360,8 @@ __device__ __forceinline__ void eval_inside(double px, double py, double pz, boo
 }
 
 // rank-1 update restricted to the entries of J that can be non-zero (compile-time MASK).
-template <int P, unsigned MASK>
-__device__ __forceinline__ void rank1_masked(double* acc, const double* J, double w, double r) {
+template <int P, unsigned MASK, typename ACC>
+__device__ __forceinline__ void rank1_masked(ACC acc, const double* J, double w, double r) {
   const double wr = w * r;
 #pragma unroll
   for (int j = 0; j < P; ++j) {
@@ -369,13 +375,13 @@ __device__ __forceinline__ void rank1_masked(double* acc, const double* J, doubl
   }
 }
 
-template <int P>
-__device__ __forceinline__ void accumulate_inside(double* acc, const Out1<P>& o) {
+template <int P, typename ACC>
+__device__ __forceinline__ void accumulate_inside(ACC acc, const Out1<P>& o) {
   constexpr int NR = P - 3;
   constexpr unsigned ROT = (1u << NR) - 1u;
-  rank1_masked<P, ROT | (1u << NR) | (1u << (NR + 2))>(acc, o.JU, o.w, o.r0);
-  rank1_masked<P, ROT | (1u << (NR + 1)) | (1u << (NR + 2))>(acc, o.JV, o.w, o.r1);
-  rank1_masked<P, ROT | (1u << (NR + 2))>(acc, o.JZ, o.w, o.r2);
+  rank1_masked<P, ROT | (1u << NR) | (1u << (NR + 2)), ACC>(acc, o.JU, o.w, o.r0);
+  rank1_masked<P, ROT | (1u << (NR + 1)) | (1u << (NR + 2)), ACC>(acc, o.JV, o.w, o.r1);
+  rank1_masked<P, ROT | (1u << (NR + 2)), ACC>(acc, o.JZ, o.w, o.r2);
 }
 
 // Running product of (1 + s) kept as mantissa in [1,2) x 2^expo: sum log(1+s) = log(prod) + expo ln 2.
@@ -484,6 +490,13 @@ constexpr int kBoxRoundFloats = kBoxFields * kThreads;
 #ifndef DIB_BOX_ROUNDS
 #define DIB_BOX_ROUNDS 8
 #endif
+#ifndef DIB_ACC_SMEM
+#define DIB_ACC_SMEM 1                        // 1: the per-lane accumulators live in shared memory ([N][32] per warp) instead of
+#endif                                        //    registers: fewer spills at 96 registers (-1.8 % kernel time); going on to 12 or
+                                              //    16 CTAs/SM (80 / 64 registers) measured slower again
+#ifndef DIB_RING
+#define DIB_RING 128                          // pending-ring entries per warp and label (power of two)
+#endif
 #ifndef DIB_GROUP_TMA
 #define DIB_GROUP_TMA 0                       // 1: undecided groups are staged by cp.async.bulk (TMA engine) into a per-warp
 #endif                                        //    double buffer one step ahead; 0: plain coalesced loads into registers.
@@ -590,7 +603,7 @@ struct LMState {
 };
 
 constexpr int kBatch = 32 * DIB_EXACT_ILP;   // entries evaluated per exact-path batch
-constexpr int kRing = 256;               // pending ring per label: < kBatch carried + at most DIB_GPS x 32 appended per step
+constexpr int kRing = DIB_RING;          // pending ring per label: < kBatch carried + at most DIB_GPS x 32 appended per step
 static_assert(kBatch + 32 * DIB_GPS <= kRing, "ring too small");
 
 // Per-warp staging buffer of one step's undecided groups (filled by bulk copies).
@@ -606,6 +619,9 @@ template <typename CT, int P>
 struct Smem {
   alignas(16) float box[kBoxRounds][kBoxRoundFloats];   // bulk-copied (TMA engine) once per problem
   Entry<CT> list[kWarps][2][kRing];                     // [label 0 | label 1] pending rings
+#if DIB_ACC_SMEM
+  double accs[kWarps][NAcc<P>::N][32];                  // per-lane accumulators (column = lane: conflict-free)
+#endif
   GroupStage<CT> gstage[kWarps][2];                     // double-buffered group staging, private to each warp
   alignas(8) uint64_t gbar[kWarps][2];                  // their mbarriers
   alignas(8) uint64_t full;                             // mbarrier of the box-table copy
@@ -668,9 +684,18 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
   const int warp = tid >> 5, lane = tid & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
   const int rounds = box_rounds(n);
+#if DIB_ACC_SMEM
+  SmemAcc acc{&sm.accs[warp][0][lane]};
+#else
   double acc[N];
+#endif
 #pragma unroll
   for (int j = 0; j < N; ++j) acc[j] = 0.0;
+#if DIB_ACC_SMEM
+  const SmemAcc acc_view = acc;
+#else
+  double* const acc_view = acc;
+#endif
   const Cam& cam = sm.cam;
   const PoseConst& pc = sm.pose;
   const ClassConst& cc = sm.cls;
@@ -783,9 +808,9 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         prod *= oa.s1;
 #endif
         renorm_product(prod, expo);
-        rank1<P>(acc, oa.J, oa.w, oa.r);
+        rank1<P, decltype(acc_view)>(acc_view, oa.J, oa.w, oa.r);
 #if DIB_EXACT_ILP == 2
-        rank1<P>(acc, ob.J, ob.w, ob.r);
+        rank1<P, decltype(acc_view)>(acc_view, ob.J, ob.w, ob.r);
 #endif
         head0 = (head0 + take) & (kRing - 1);
         pend0 -= take;
@@ -806,9 +831,9 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         prod *= oa.s1;
 #endif
         renorm_product(prod, expo);
-        accumulate_inside<P>(acc, oa);
+        accumulate_inside<P, decltype(acc_view)>(acc_view, oa);
 #if DIB_EXACT_ILP == 2
-        accumulate_inside<P>(acc, ob);
+        accumulate_inside<P, decltype(acc_view)>(acc_view, ob);
 #endif
         head1 = (head1 + take) & (kRing - 1);
         pend1 -= take;
@@ -887,9 +912,9 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         prod *= oa.s1;
 #endif
         renorm_product(prod, expo);
-        rank1<P>(acc, oa.J, oa.w, oa.r);
+        rank1<P, decltype(acc_view)>(acc_view, oa.J, oa.w, oa.r);
 #if DIB_EXACT_ILP == 2
-        rank1<P>(acc, ob.J, ob.w, ob.r);
+        rank1<P, decltype(acc_view)>(acc_view, ob.J, ob.w, ob.r);
 #endif
         head0 = (head0 + take) & (kRing - 1);
         pend0 -= take;
@@ -910,9 +935,9 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         prod *= oa.s1;
 #endif
         renorm_product(prod, expo);
-        accumulate_inside<P>(acc, oa);
+        accumulate_inside<P, decltype(acc_view)>(acc_view, oa);
 #if DIB_EXACT_ILP == 2
-        accumulate_inside<P>(acc, ob);
+        accumulate_inside<P, decltype(acc_view)>(acc_view, ob);
 #endif
         head1 = (head1 + take) & (kRing - 1);
         pend1 -= take;
@@ -944,6 +969,15 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
   // [N][33] scratch: lane j sums accumulator j over lanes 0..31 in order, then thread j sums the
   // warps in order.  (A loop over shared memory instead of ~300 unrolled shuffles: this epilogue
   // runs once per pass and its code size matters more than its speed.)
+#if DIB_ACC_SMEM
+  __syncwarp();
+  if (lane < N) {                                   // the accumulators already sit in shared memory as [N][32]
+    double v = 0.0;
+#pragma unroll 4
+    for (int l = 0; l < 32; ++l) v += sm.accs[warp][lane][l];
+    sm.red[warp][lane] = v;
+  }
+#else
   double* scratch = reinterpret_cast<double*>(sm.list[warp]);
   static_assert(sizeof(Entry<CT>) * 2 * kRing >= sizeof(double) * N * 33, "ring too small for the reduction scratch");
   __syncwarp();
@@ -956,6 +990,7 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
     for (int l = 0; l < 32; ++l) v += scratch[lane * 33 + l];
     sm.red[warp][lane] = v;
   }
+#endif
   __syncthreads();
   if (tid < N) {
     double v = sm.red[0][tid];
