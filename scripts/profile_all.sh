@@ -22,7 +22,7 @@ for f in ("bench_${tag}.json", "bench_${tag}_reference.json", "bench_${tag}_sing
         d = json.load(open("gpurun_out/" + f))
         r = d.get("roofline", {})
         print(f, "value %.1f e2e %.1f frac %s kernel_ms %s" % (d["value"], d["e2e"]["value"], r.get("frac"), r.get("kernel_ms")))
-        if "ops" in d: print("  ops:", {k: (round(v["us"], 1), round(v.get("frac", v.get("frac_algorithmic")), 3)) for k, v in d["ops"].items() if isinstance(v, dict) and "us" in v})
+        if "ops" in d: print("  ops:", {k: (round(v["us"], 1), round(v.get("frac", v.get("frac_algorithmic")) or 0, 3)) for k, v in d["ops"].items() if isinstance(v, dict) and "us" in v})
         if "parity" in d: print("  parity:", {k: v for k, v in d["parity"].items() if k not in ("note", "gate")})
         if "cpu_baseline" in d: print("  cpu:", d["cpu_baseline"]["value"], d["cpu_baseline"]["cores"])
     except Exception as e:
