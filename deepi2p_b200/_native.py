@@ -18,6 +18,7 @@ EXPORTS = (
     "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32",
     "frustum_inside_mask_f32", "pose_error_batch",
     "index_max_forward", "ball_query_forward", "ball_query_xyz_workspace_bytes", "ball_query_xyz_forward",
+    "cluster_assign_workspace_bytes", "cluster_assign_forward",
 )
 
 
@@ -80,6 +81,10 @@ def load():
     lib.ball_query_xyz_workspace_bytes.argtypes = [i32, i32]
     lib.ball_query_xyz_forward.restype = i32
     lib.ball_query_xyz_forward.argtypes = [vp, vp, _c.c_float, vp, i32, i32, i32, i32, vp, sz, vp]
+    lib.cluster_assign_workspace_bytes.restype = sz
+    lib.cluster_assign_workspace_bytes.argtypes = [i32, i32]
+    lib.cluster_assign_forward.restype = i32
+    lib.cluster_assign_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     lib.ball_query_forward.restype = i32
     lib.ball_query_forward.argtypes = [vp, _c.c_float, vp, i32, i32, i32, i32, vp]
     _lib = lib

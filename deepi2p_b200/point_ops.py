@@ -84,3 +84,44 @@ def ball_query_xyz_forward(points, nodes, radius, K):
                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
     _native.check(rc, "ball_query_xyz_forward")
     return out
+
+
+_ca_ws = {}
+
+
+def cluster_assign_forward(pc, node, k=1, want_centers=True):
+    """Nearest-node clustering of models/networks_pc.py:60-85 without its B x N x Ma intermediates.
+
+    pc [B,3,N], node [B,3,M] float32 CUDA.  Returns dict(min_k_idx int32 [B,N,k] (nearest first), min_idx int32
+    [B,N] (feed it to index_max_forward), count int32 [B,M] (mask_row_max = count > 0), cluster_mean [B,3,M],
+    pc_centers [B,3,N], pc_decentered [B,3,N]).  Forward only, like the reference (everything here is
+    detached there: :76,:82)."""
+    _check_input(pc, "pc", torch.float32)
+    _check_input(node, "node", torch.float32)
+    if pc.dim() != 3 or node.dim() != 3 or pc.shape[1] != 3 or node.shape[1] != 3 or pc.shape[0] != node.shape[0]:
+        raise RuntimeError("pc must be [B,3,N] and node [B,3,M]")
+    lib = _native.load()
+    B, _, N = pc.shape
+    M = node.shape[2]
+    k = int(k)
+    dev = pc.device
+    with torch.cuda.device(dev):
+        need = lib.cluster_assign_workspace_bytes(B, M)
+        ws = _ca_ws.get(dev.index)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
+            _ca_ws[dev.index] = ws
+        topk = torch.empty((B, N, k), dtype=torch.int32, device=dev)
+        min_idx = torch.empty((B, N), dtype=torch.int32, device=dev)
+        count = torch.empty((B, M), dtype=torch.int32, device=dev)
+        mean = torch.empty((B, 3, M), dtype=torch.float32, device=dev)
+        centers = torch.empty((B, 3, N), dtype=torch.float32, device=dev) if want_centers else None
+        dec = torch.empty((B, 3, N), dtype=torch.float32, device=dev) if want_centers else None
+        rc = lib.cluster_assign_forward(pc.data_ptr(), node.data_ptr(), B, N, M, k, topk.data_ptr(), min_idx.data_ptr(),
+                                        count.data_ptr(), mean.data_ptr(),
+                                        centers.data_ptr() if want_centers else 0,
+                                        dec.data_ptr() if want_centers else 0, ws.data_ptr(), ws.numel(),
+                                        torch.cuda.current_stream().cuda_stream)
+    _native.check(rc, "cluster_assign_forward")
+    return dict(min_k_idx=topk, min_idx=min_idx, count=count, cluster_mean=mean, pc_centers=centers,
+                pc_decentered=dec)

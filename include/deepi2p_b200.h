@@ -161,6 +161,22 @@ size_t ball_query_xyz_workspace_bytes(int B, int N);
 int ball_query_xyz_forward(const float* points, const float* nodes, float radius, int32_t* out, int B, int M, int N,
                            int K, void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
+/* ---- clustering front-end of the point-cloud encoder (replaces the B x N x Ma
+ * intermediates of models/networks_pc.py:60-85) -------------------------------------------------
+ * pc [B][3][N] f32, node [B][3][M] f32 [dev].  Outputs [dev]:
+ *   min_k_idx [B][N][k] i32  k nearest nodes of each point, nearest first (torch.topk(diff, k, largest=False), :63-64);
+ *                            key ((dx*dx + dy*dy) + dz*dz) in float32 without fma, ties -> lower node index
+ *   min_idx   [B][N]    i32  = min_k_idx[..][0], the `index` argument of index_max (:65,:88-90)
+ *   count     [B][M]    i32  points per node (mask_row_sum, :69-72; mask_row_max = count > 0)
+ *   cluster_mean [B][3][M] f32 = float(sum_fixed * 2^-24) / (float(count) + 1e-5f), sum_fixed = exact int64 sum
+ *                            of rint(x * 2^24) -- order independent (:74-76)
+ *   pc_centers, pc_decentered [B][3][N] f32 (each may be NULL): cluster_mean gathered by min_idx, pc - centers (:78-82)
+ * 1 <= k <= min(8, M), M <= 2048.  workspace: [dev], 8-byte aligned, >= cluster_assign_workspace_bytes(B, M). */
+size_t cluster_assign_workspace_bytes(int B, int M);
+int cluster_assign_forward(const float* pc, const float* node, int B, int N, int M, int k, int32_t* min_k_idx,
+                           int32_t* min_idx, int32_t* count, float* cluster_mean, float* pc_centers,
+                           float* pc_decentered, void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -241,3 +241,31 @@ def ball_query_xyz(points, nodes, radius, K):
             if len(hits):
                 out[b, m] = [hits[i] if i < len(hits) else hits[(i - len(hits)) % len(hits)] for i in range(K)]
     return out
+
+
+def cluster_assign(pc, node, k):
+    """Oracle for cluster_assign_forward: the clustering front-end of models/networks_pc.py:60-85.
+
+    pc [B,3,N], node [B,3,M].  Ordering key = float32 ((dx*dx + dy*dy) + dz*dz) (numpy float32 arithmetic has no
+    fma), stable sort => ties go to the lower node index (torch.topk leaves them unspecified; sqrt is monotone).
+    Sums are exact fixed point (rint(x * 2^24) in int64), mean = float32(sum * 2^-24) / (float32(count) + 1e-5f)."""
+    p = np.asarray(pc, dtype=np.float32)
+    q = np.asarray(node, dtype=np.float32)
+    B, _, N = p.shape
+    M = q.shape[2]
+    d = p[:, :, :, None] - q[:, :, None, :]                      # [B,3,N,M], point - node
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    order = np.argsort(d2, axis=2, kind="stable")[:, :, :k].astype(np.int32)
+    min_idx = order[:, :, 0]
+    count = np.zeros((B, M), dtype=np.int32)
+    sums = np.zeros((B, 3, M), dtype=np.int64)
+    fixed = np.rint(p.astype(np.float64) * 16777216.0).astype(np.int64)
+    for b in range(B):
+        np.add.at(count[b], min_idx[b], 1)
+        for a in range(3):
+            np.add.at(sums[b, a], min_idx[b], fixed[b, a])
+    num = (sums.astype(np.float64) * (1.0 / 16777216.0)).astype(np.float32)
+    mean = num / (count.astype(np.float32)[:, None, :] + np.float32(1e-5))
+    centers = np.take_along_axis(mean, np.broadcast_to(min_idx[:, None, :].astype(np.int64), (B, 3, N)), axis=2)
+    return dict(min_k_idx=order, min_idx=min_idx.copy(), count=count, cluster_mean=mean.astype(np.float32),
+                pc_centers=centers.astype(np.float32), pc_decentered=(p - centers).astype(np.float32))

@@ -428,3 +428,31 @@ def test_inside_mask_and_pose_error_ops(cuda):
         assert ok[i] == int(t_want < 2 and r_want < 5)
     assert abs(out["success_rate"].item() - ok.mean()) < 1e-12
     assert 0 < ok.sum() < 64
+
+
+def test_register_directory_legacy_handoff(cuda, tmp_path):
+    """8(f) N2: a directory in the reference's file-triple layout gives the same poses as the in-memory
+    contract, plus the result files and summary of registration_lsq.py:396-398 / registration_result_analysis.py."""
+    from deepi2p_b200 import handoff
+
+    S, n = 5, 2048
+    samples = [small_sample(700 + s, n) for s in range(S)]
+    for s, smp in enumerate(samples):
+        handoff.save_record(str(tmp_path / "data"), "%06d_%02d" % (s * 30, 0), smp["points"], smp["pred"], smp["gt"],
+                            smp["pred"], smp["gt"], smp["K"], smp["P_gt"][:3])
+    res = handoff.register_directory(str(tmp_path / "data"), syn.KITTI["H"], syn.KITTI["W"], n_inits=12, seed=3,
+                                     out_dir=str(tmp_path / "out"))
+    xyz = torch.from_numpy(np.stack([smp["points"].astype(np.float32) for smp in samples])).cuda()
+    pred = torch.from_numpy(np.stack([smp["pred"].astype(np.int8) for smp in samples])).cuda()
+    K = np.stack([smp["K"].reshape(9) for smp in samples])
+    ref = frustum.register_batch(xyz, pred, n, K, syn.KITTI["H"], syn.KITTI["W"], n_inits=12, seed=3)
+    np.testing.assert_array_equal(res["P_pred"], ref["P"].cpu().numpy())
+    np.testing.assert_array_equal(res["cost"], ref["cost"].cpu().numpy())
+    np.testing.assert_array_equal(np.load(tmp_path / "out" / "P_pred_all_np.npy"), res["P_pred"])
+    np.testing.assert_array_equal(np.load(tmp_path / "out" / "P_gt_all_np.npy"),
+                                  np.stack([smp["P_gt"] for smp in samples]))
+    for s, smp in enumerate(samples):
+        t, r = oracle.pose_diff(res["P_pred"][s], smp["P_gt"])
+        assert abs(t - res["t_err"][s]) < 1e-9 and abs(r - res["r_err"][s]) < 1e-7
+    sm = res["summary"]
+    assert sm["n"] == S and 0.0 <= sm["success_rate"] <= 1.0 and np.isfinite(sm["rte_mean"])

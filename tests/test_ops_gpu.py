@@ -182,3 +182,65 @@ def test_ball_query_xyz_grid_hash(cuda, B, M, N, K, cube, radius):
     d2 = ((d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]).astype(np.float32)
     dense = run_ball_query(d2, float(np.float32(radius) * np.float32(radius)), K)
     np.testing.assert_array_equal(got, dense)
+
+
+def _cluster_check(pts, nodes, k):
+    got = point_ops.cluster_assign_forward(torch.from_numpy(pts).cuda(), torch.from_numpy(nodes).cuda(), k)
+    want = oracle.cluster_assign(pts, nodes, k)
+    for name in ("min_k_idx", "min_idx", "count", "cluster_mean", "pc_centers", "pc_decentered"):
+        np.testing.assert_array_equal(got[name].cpu().numpy(), want[name], err_msg=name)     # bit-exact, floats too
+    return got, want
+
+
+@pytest.mark.parametrize("B,N,M,k", [(3, 5000, 128, 3), (8, 20480, 128, 3), (2, 1024, 1, 1), (1, 777, 8, 8),
+                                     (1, 3000, 2048, 5), (2, 1, 4, 2)])
+def test_cluster_assign_matches_oracle(cuda, B, N, M, k):
+    """8(f) N4: nearest-node clustering of networks_pc.py:60-85, every output bit-exact against the oracle."""
+    rng = np.random.default_rng(B * 1000 + N + M + k)
+    pts = rng.uniform(-40, 40, (B, 3, N)).astype(np.float32)
+    nodes = rng.uniform(-40, 40, (B, 3, M)).astype(np.float32)
+    got, want = _cluster_check(pts, nodes, k)
+    assert int(got["count"].sum()) == B * N
+    # feeds index_max exactly like the encoder does (:88-90)
+    C = 8
+    feat = rng.standard_normal((B, C, N)).astype(np.float32)
+    idx = point_ops.index_max_forward(torch.from_numpy(feat).cuda(), got["min_idx"], M)
+    np.testing.assert_array_equal(idx.cpu().numpy(), oracle.index_max(feat, want["min_idx"], M))
+
+
+def test_cluster_assign_ties_empty_nodes_and_determinism(cuda):
+    rng = np.random.default_rng(5)
+    # lattice points and lattice nodes: masses of exact distance ties; duplicated nodes; a node nobody picks
+    pts = rng.integers(-4, 5, (2, 3, 4096)).astype(np.float32)
+    nodes = rng.integers(-4, 5, (2, 3, 32)).astype(np.float32)
+    nodes[:, :, 5] = nodes[:, :, 2]                      # duplicate: the lower index must win every time
+    nodes[:, :, 9] = 1e4                                 # empty cluster: count 0, mean 0 (:75, 0 / 1e-5)
+    got, want = _cluster_check(pts, nodes, 4)
+    assert (got["count"][:, 5] == 0).all() and (got["count"][:, 9] == 0).all()
+    assert (got["cluster_mean"][:, :, 9] == 0).all()
+    again = point_ops.cluster_assign_forward(torch.from_numpy(pts).cuda(), torch.from_numpy(nodes).cuda(), 4)
+    for name in got:
+        assert torch.equal(got[name], again[name]), name   # atomics land in any order, the result may not change
+    # against the reference's own formulas in torch (float tree sums: tolerance, indices where unambiguous)
+    p, nd = torch.from_numpy(pts).cuda(), torch.from_numpy(nodes).cuda()
+    diff = torch.norm(p.unsqueeze(3) - nd.unsqueeze(2), dim=1, p=2)
+    ref_d = torch.gather(diff, 2, got["min_k_idx"].long())
+    top_d, _ = torch.topk(diff, k=4, dim=2, largest=False, sorted=True)
+    assert torch.equal(ref_d, top_d)                     # same distances as torch.topk picks (ties may permute ids)
+    mask = torch.eq(got["min_idx"].long().unsqueeze(2), torch.arange(32, device="cuda").view(1, 1, 32)).float()
+    cm = (p.unsqueeze(3) * mask.unsqueeze(1)).sum(2) / (mask.sum(1).unsqueeze(1) + 1e-5)
+    assert (cm - got["cluster_mean"]).abs().max().item() < 1e-4
+
+
+def test_cluster_assign_argument_checks(cuda):
+    p = torch.zeros(1, 3, 16, device="cuda")
+    nd = torch.zeros(1, 3, 4, device="cuda")
+    from deepi2p_b200 import _native
+    with pytest.raises(_native.NativeError):
+        point_ops.cluster_assign_forward(p, nd, 5)        # k > M
+    with pytest.raises(_native.NativeError):
+        point_ops.cluster_assign_forward(p, torch.zeros(1, 3, 16, device="cuda"), 9)    # k > 8
+    with pytest.raises(RuntimeError):
+        point_ops.cluster_assign_forward(p.cpu(), nd, 1)
+    out = point_ops.cluster_assign_forward(torch.zeros(2, 3, 0, device="cuda"), torch.ones(2, 3, 4, device="cuda"), 2)
+    assert out["min_k_idx"].shape == (2, 0, 2) and (out["count"] == 0).all() and (out["cluster_mean"] == 0).all()
