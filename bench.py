@@ -521,6 +521,28 @@ def bench_ops(torch, dev, peak):
         "shape": {"B": B, "C": C, "M": C, "N": N, "K": K},
         "l2": "two alternating 268 MB input sets per op (> L2), no flush; 10 back-to-back launches per event pair",
     }
+    # 8(f) N4: clustering front-end at the shipped encoder shape (kitti/options.py:28-35): B=8, N=20480, Ma=128, k=3
+    cb, cn, cm, ck = 8, 20480, 128, 3
+    cpc = [(torch.rand((cb, 3, cn), device=dev, generator=g) * 80 - 40) for _ in range(2)]
+    cnode = [c[:, :, torch.randperm(cn, device=dev, generator=g)[:cm]].contiguous() for c in cpc]
+    ca_ms = t(lambda i: point_ops.cluster_assign_forward(cpc[i], cnode[i], ck))
+
+    def torch_clustering(i):            # the reference's formulation, networks_pc.py:60-82 (torch library ops)
+        pc, node = cpc[i], cnode[i]
+        diff = torch.norm(pc.unsqueeze(3) - node.unsqueeze(2), dim=1, p=2)
+        _, mk = torch.topk(diff, k=ck, dim=2, largest=False, sorted=True)
+        mi = mk[:, :, 0]
+        mask = torch.eq(mi.unsqueeze(2), torch.arange(cm, device=dev).view(1, 1, cm))
+        mf = mask.unsqueeze(1).float()
+        mean = torch.sum(pc.unsqueeze(3) * mf, dim=2) / (torch.sum(mf, dim=2) + 1e-5)
+        return pc - torch.gather(mean, index=mi.unsqueeze(1).expand(cb, 3, cn), dim=2)
+
+    res["cluster_assign"] = {"us": ca_ms * 1e3, "reference_torch_us": 1e3 * t(torch_clustering, 2, 3),
+                             "shape": {"B": cb, "N": cn, "Ma": cm, "k": ck},
+                             "bytes": (12 * 2 + 4 * ck + 4 + 24) * cb * cn,
+                             "note": "3 launches (assign+sums, means, decenter); inputs are L2-resident at this size, "
+                                     "so this is a latency/issue-bound op, not an HBM one; the torch formulation "
+                                     "materialises several B x N x Ma tensors"}
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import build_ref

@@ -36,7 +36,12 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB
-    if not os.path.exists(path) or _build.is_stale():
+    override = os.environ.get("DIB_LIB_OVERRIDE")       # tuning aid: a prebuilt variant of the same library
+    if override:
+        if not os.path.exists(override):
+            raise NativeError(f"DIB_LIB_OVERRIDE={override} does not exist")
+        path = override
+    elif not os.path.exists(path) or _build.is_stale():
         try:
             _build.build()
         except Exception as e:  # noqa: BLE001 - turn any build problem into a loud, specific error

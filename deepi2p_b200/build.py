@@ -41,7 +41,19 @@ def is_stale():
     return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False, extra=()):
+def build(force=False, verbose=False, extra=(), out=None):
+    """Compile the library in-tree.  `out` names a variant file (lib/variants/<out>.so) instead of the default
+    library; variants are a tuning aid (scripts/ab_prebuilt.sh) selected at run time with DIB_LIB_OVERRIDE."""
+    if out is not None:
+        vdir = os.path.join(LIBDIR, "variants")
+        os.makedirs(vdir, exist_ok=True)
+        target = os.path.join(vdir, out + ".so")
+        srcs = [os.path.join(CSRC, s) for s in SOURCES]
+        cmd = [nvcc_path(), *NVCC_FLAGS, *extra, *os.environ.get("DIB_NVCC_EXTRA", "").split(), "-o", target, *srcs]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+        return target
     if not force and not is_stale():
         return LIB
     os.makedirs(LIBDIR, exist_ok=True)
@@ -57,4 +69,5 @@ def build(force=False, verbose=False, extra=()):
 
 if __name__ == "__main__":
     extra = ["-Xptxas", "-v"] if "--ptxas" in sys.argv else []
-    print(build(force="--force" in sys.argv or bool(extra), verbose=True, extra=extra))
+    out = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else None
+    print(build(force="--force" in sys.argv or bool(extra), verbose=True, extra=extra, out=out))

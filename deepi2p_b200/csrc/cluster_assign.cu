@@ -27,13 +27,14 @@
 namespace dib {
 
 constexpr int kCaThreads = 256;
-constexpr int kCaPointsPerThread = 4;
+constexpr int kCaPointsPerThread = 1;
 constexpr int kCaMaxK = 8;
 constexpr int kCaMaxNodes = 2048;
 constexpr double kCaFixedScale = 16777216.0;        // 2^24
 
+template <int K>
 __global__ void __launch_bounds__(kCaThreads)
-    cluster_assign_kernel(const float* __restrict__ pc, const float* __restrict__ node, int N, int M, int k,
+    cluster_assign_kernel(const float* __restrict__ pc, const float* __restrict__ node, int N, int M,
                           int32_t* __restrict__ topk, int32_t* __restrict__ min_idx, int32_t* __restrict__ count,
                           unsigned long long* __restrict__ sums) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -53,30 +54,28 @@ __global__ void __launch_bounds__(kCaThreads)
     const int n = base + q * kCaThreads + tid;
     if (n >= N) break;
     const float x = px[n], y = px[(size_t)N + n], z = px[2 * (size_t)N + n];
-    float bd[kCaMaxK];
-    int bi[kCaMaxK];
+    float bd[K];
+    int bi[K];
 #pragma unroll
-    for (int j = 0; j < kCaMaxK; ++j) { bd[j] = FLT_MAX * 2.0f; bi[j] = j; }      // +inf, never beaten by inf / NaN
-#pragma unroll 2
+    for (int j = 0; j < K; ++j) { bd[j] = __int_as_float(0x7f800000); bi[j] = j; }   // +inf: never beaten by inf / NaN
+#pragma unroll 4
     for (int m = 0; m < M; ++m) {
       const float dx = __fsub_rn(x, s_node[m]), dy = __fsub_rn(y, s_node[M + m]), dz = __fsub_rn(z, s_node[2 * M + m]);
       const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-      bool worse = true;                                                           // d2 does not beat slot j
+      if (!(d2 < bd[K - 1])) continue;                  // strict: on a tie the earlier (lower) node stays
+      // sorted insert from the back; all indices are compile-time, so bd / bi stay in registers
 #pragma unroll
-      for (int j = 0; j < kCaMaxK; ++j) if (j == k - 1) worse = !(d2 < bd[j]);
-      if (worse) continue;
-      bool placed = false;
-#pragma unroll
-      for (int j = kCaMaxK - 1; j >= 0; --j) {
-        if (j < k && !placed) {
-          if (j > 0 && d2 < bd[j > 0 ? j - 1 : 0]) { bd[j] = bd[j > 0 ? j - 1 : 0]; bi[j] = bi[j > 0 ? j - 1 : 0]; }
-          else { bd[j] = d2; bi[j] = m; placed = true; }
-        }
+      for (int j = K - 1; j >= 1; --j) {
+        const bool shift = d2 < bd[j - 1];
+        const bool here = !shift && d2 < bd[j];
+        bd[j] = shift ? bd[j - 1] : (here ? d2 : bd[j]);
+        bi[j] = shift ? bi[j - 1] : (here ? m : bi[j]);
       }
+      if (d2 < bd[0]) { bd[0] = d2; bi[0] = m; }
     }
-    int32_t* o = topk + ((size_t)b * N + n) * k;
+    int32_t* o = topk + ((size_t)b * N + n) * K;
 #pragma unroll
-    for (int j = 0; j < kCaMaxK; ++j) if (j < k) o[j] = bi[j];
+    for (int j = 0; j < K; ++j) o[j] = bi[j];
     const int m0 = bi[0];
     min_idx[(size_t)b * N + n] = m0;
     atomicAdd(&s_cnt[m0], 1);
@@ -151,12 +150,20 @@ int cluster_assign_forward(const float* pc, const float* node, int B, int N, int
   DIB_CHECK_CUDA(cudaMemsetAsync(count, 0, (size_t)B * M * sizeof(int32_t), stream));
   if (N > 0) {
     const size_t smem = (size_t)M * (3 * sizeof(unsigned long long) + 3 * sizeof(float) + sizeof(int));
-    if (smem > 48 * 1024)
-      DIB_CHECK_CUDA(cudaFuncSetAttribute(cluster_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((size_t)kCaMaxNodes * 40)));
     const int per_cta = kCaThreads * kCaPointsPerThread;
     dim3 grid((N + per_cta - 1) / per_cta, B);
-    cluster_assign_kernel<<<grid, kCaThreads, smem, stream>>>(pc, node, N, M, k, min_k_idx, min_idx, count, sums);
+#define DIB_CA_LAUNCH(KK)                                                                                         \
+  case KK:                                                                                                        \
+    if (smem > 48 * 1024)                                                                                         \
+      DIB_CHECK_CUDA(cudaFuncSetAttribute(cluster_assign_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          (int)((size_t)kCaMaxNodes * 40)));                                      \
+    cluster_assign_kernel<KK><<<grid, kCaThreads, smem, stream>>>(pc, node, N, M, min_k_idx, min_idx, count, sums); \
+    break;
+    switch (k) {
+      DIB_CA_LAUNCH(1) DIB_CA_LAUNCH(2) DIB_CA_LAUNCH(3) DIB_CA_LAUNCH(4)
+      DIB_CA_LAUNCH(5) DIB_CA_LAUNCH(6) DIB_CA_LAUNCH(7) DIB_CA_LAUNCH(8)
+    }
+#undef DIB_CA_LAUNCH
     DIB_CHECK_CUDA(cudaGetLastError());
   }
   const int total = B * 3 * M;

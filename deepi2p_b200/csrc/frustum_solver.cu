@@ -497,6 +497,13 @@ constexpr int kBoxRoundFloats = kBoxFields * kThreads;
 #ifndef DIB_RING
 #define DIB_RING 128                          // pending-ring entries per warp and label (power of two)
 #endif
+#ifndef DIB_PACKED
+#define DIB_PACKED 1                          // 1: frustum_boxes_kernel also writes a packed {x, y, z, label} record per point into the
+#endif                                        //    workspace and the solver loads an undecided group's points with ONE 16-byte load per lane
+                                              //    instead of four (the x/y/z/label arrays of the canonical record are then read once per launch)
+#ifndef DIB_GROUP_PIPE
+#define DIB_GROUP_PIPE 0                      // 1: software-pipeline the undecided-group loads one step ahead (registers)
+#endif
 #ifndef DIB_GROUP_TMA
 #define DIB_GROUP_TMA 0                       // 1: undecided groups are staged by cp.async.bulk (TMA engine) into a per-warp
 #endif                                        //    double buffer one step ahead; 0: plain coalesced loads into registers.
@@ -518,11 +525,18 @@ constexpr int kBoxRounds = DIB_BOX_SMEM ? DIB_BOX_ROUNDS : 1;   // rounds reside
 
 __host__ __device__ inline int box_rounds(int n) { return (((n + 31) >> 5) + kThreads - 1) / kThreads; }
 
+// Self-contained record of a point: the element of the packed per-launch copy (DIB_PACKED) and of the
+// per-warp rings of maybe-active points.
+template <typename CT> struct Entry;
+template <> struct alignas(16) Entry<float> { float x, y, z; int lab; };
+template <> struct alignas(16) Entry<double> { double x, y, z; long long lab; };
+
 template <typename CT>
 __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict__ xyz,
                                                             const int8_t* __restrict__ label,
                                                             const int32_t* __restrict__ n_pts, int n_stride,
-                                                            int rounds_max, float* __restrict__ table) {
+                                                            int rounds_max, float* __restrict__ table,
+                                                            Entry<CT>* __restrict__ packed) {
   const int s = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -531,16 +545,21 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
   const int i = gid * 32 + lane;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   int lab = -1;
+  Entry<CT> e;
+  e.x = 0; e.y = 0; e.z = 0; e.lab = -1;
   if (i < n) {
     lab = label[(size_t)s * n_stride + i];
     if (lab == 0 || lab == 1) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double v = (double)xyz[((size_t)s * 3 + c) * n_stride + i];
-        lo[c] = v; hi[c] = v;
-      }
+      e.x = xyz[((size_t)s * 3 + 0) * n_stride + i];
+      e.y = xyz[((size_t)s * 3 + 1) * n_stride + i];
+      e.z = xyz[((size_t)s * 3 + 2) * n_stride + i];
+      e.lab = lab;
+      lo[0] = hi[0] = (double)e.x; lo[1] = hi[1] = (double)e.y; lo[2] = hi[2] = (double)e.z;
     }
   }
+  // packed copy: every slot of the sample's rounds x kThreads x 32 grid is written (padding and ignored labels
+  // as label -1), so the solver needs no bounds test
+  if (packed) packed[(size_t)s * rounds_max * (kThreads * 32) + i] = e;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -575,10 +594,6 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
 // ------------------------------------------------------------------------------------------
 // Shared-memory layout of one CTA.
 // ------------------------------------------------------------------------------------------
-// Self-contained record of a maybe-active point, queued per warp and label until 64 are pending.
-template <typename CT> struct Entry;
-template <> struct alignas(16) Entry<float> { float x, y, z; int lab; };
-template <> struct alignas(16) Entry<double> { double x, y, z; long long lab; };
 
 struct LsSample {
   double x, value, gradient;
@@ -677,8 +692,8 @@ __device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst&
 // `boxes_resident` says the sample's whole table already sits in sm.box.
 // ------------------------------------------------------------------------------------------
 template <typename CT, int P>
-__device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, int n_stride, int n,
-                               const float* box_s, bool boxes_resident, uint32_t& box_phase, uint32_t& gphase) {
+__device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, const Entry<CT>* pk_s,
+                               int n_stride, int n, const float* box_s, bool boxes_resident, uint32_t& box_phase, uint32_t& gphase) {
   constexpr int N = NAcc<P>::N;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -876,26 +891,48 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
     // Undecided groups are taken DIB_GPS at a time.  Their loads are issued first, then the pending
     // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
     // (independent instruction streams) and appended.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
-#pragma unroll 1
-    do {
-      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-      int glab[DIB_GPS];
-      const bool have = mask != 0;
-      if (have) {
+    auto load_groups = [&](CT* lx, CT* ly, CT* lz, int* ll) -> bool {
+      const bool any = mask != 0;
+      if (any) {
 #pragma unroll
         for (int u = 0; u < DIB_GPS; ++u) {
-          glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
+          ll[u] = -1; lx[u] = 0; ly[u] = 0; lz[u] = 0;
           if (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
             const int i = (r * kThreads + b * kWarps + warp) * 32 + lane;      // this lane's point
+#if DIB_PACKED
+            const Entry<CT> e = pk_s[i];
+            ll[u] = (int)e.lab; lx[u] = e.x; ly[u] = e.y; lz[u] = e.z;
+#else
             if (i < n) {
-              glab[u] = lab_s[i];
-              gx[u] = xyz_s[i]; gy[u] = xyz_s[n_stride + i]; gz[u] = xyz_s[2 * (size_t)n_stride + i];
+              ll[u] = lab_s[i];
+              lx[u] = xyz_s[i]; ly[u] = xyz_s[n_stride + i]; lz[u] = xyz_s[2 * (size_t)n_stride + i];
             }
+#endif
           }
         }
       }
+      return any;
+    };
+#if DIB_GROUP_PIPE
+    // register software pipeline: the NEXT DIB_GPS groups are loaded before the current ones are classified,
+    // so the L2 latency of a group is covered by the classification of the previous one as well
+    CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+    int glab[DIB_GPS];
+    bool have = load_groups(gx, gy, gz, glab);
+#endif
+#pragma unroll 1
+    do {
+#if DIB_GROUP_PIPE
+      CT nx[DIB_GPS], ny[DIB_GPS], nz[DIB_GPS];
+      int nlab[DIB_GPS];
+      const bool nhave = load_groups(nx, ny, nz, nlab);
+#else
+      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+      int glab[DIB_GPS];
+      const bool have = load_groups(gx, gy, gz, glab);
+#endif
 #pragma unroll 1
       while (pend0 >= threshold) {
         __syncwarp();
@@ -959,8 +996,17 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
           pend0 += __popc(m0);
           pend1 += __popc(m1);
         }
-            }
+      }
+#if DIB_GROUP_PIPE
+      if (nhave) {
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) { gx[u] = nx[u]; gy[u] = ny[u]; gz[u] = nz[u]; glab[u] = nlab[u]; }
+      }
+      have = nhave;
+    } while (have);
+#else
     } while (mask);
+#endif
 #endif
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
@@ -1493,6 +1539,7 @@ struct SolveArgs {
   int32_t* stats_all;   // [S*I*4]
   unsigned int* queue;  // problem counter
   const float* boxes;   // [S][rounds_max][8][kThreads] box table
+  const void* packed;   // [S][rounds_max * kThreads * 32] Entry<CT> (DIB_PACKED) or NULL
   int rounds_max;
   const int32_t* perm;  // [S][I] inits of each sample, longest-predicted first
   int chunk;            // samples per scheduling chunk
@@ -1558,6 +1605,7 @@ __global__ void __launch_bounds__(kThreads, (P == 4) ? DIB_MINBLOCKS4 : DIB_MINB
     const int s = prob / a.I;
     const CT* xyz_s = reinterpret_cast<const CT*>(a.xyz) + (size_t)s * 3 * a.n_stride;
     const int8_t* lab_s = a.label + (size_t)s * a.n_stride;
+    const Entry<CT>* pk_s = reinterpret_cast<const Entry<CT>*>(a.packed) + (size_t)s * a.rounds_max * (kThreads * 32);
     const float* box_s = a.boxes + (size_t)s * a.rounds_max * kBoxRoundFloats;
     const int n = a.n_pts ? a.n_pts[s] : a.n_stride;
     if (tid == 0) {
@@ -1569,7 +1617,7 @@ __global__ void __launch_bounds__(kThreads, (P == 4) ? DIB_MINBLOCKS4 : DIB_MINB
     const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);   // overlaps thread 0's set-up
     __syncthreads();
     while (sm.go == LM_EVAL) {
-      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, a.n_stride, n, box_s, resident, box_phase, gphase);
+      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, pk_s, a.n_stride, n, box_s, resident, box_phase, gphase);
       if (tid == 0) {
         const int rc = lm_consume<P>(sm.lm, sm.tot);
         sm.go = rc;
@@ -1635,7 +1683,8 @@ template <typename CT, int P>
 __global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xyz, const int8_t* label,
                                                                      const int32_t* n_pts, int n_stride,
                                                                      const double* K9, const double* x, double H,
-                                                                     double W, const float* boxes, int rounds_max,
+                                                                     double W, const float* boxes,
+                                                                     const Entry<CT>* packed, int rounds_max,
                                                                      double* cost_out, double* grad_out,
                                                                      double* JtJ_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1656,8 +1705,8 @@ __global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xy
   const float* box_s = boxes + (size_t)s * rounds_max * kBoxRoundFloats;
   const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);
   __syncthreads();
-  evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride, n_stride, n, box_s, resident,
-                        box_phase, gphase);
+  evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride,
+                        packed + (size_t)s * rounds_max * (kThreads * 32), n_stride, n, box_s, resident, box_phase, gphase);
   if (tid == 0) {
     cost_out[s] = sm.tot[0];
     for (int j = 0; j < 6; ++j) grad_out[(size_t)s * 6 + j] = (j < P) ? sm.tot[1 + j] : 0.0;
@@ -1698,16 +1747,25 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static size_t box_table_bytes(int S, int n_stride) {
   return align_up((size_t)(S > 0 ? S : 0) * box_rounds(n_stride) * kBoxRoundFloats * sizeof(float), 256);
 }
+// packed per-launch copy of the clouds; sized for the wider (f64) record so one workspace serves both ABIs
+static size_t packed_bytes(int S, int n_stride) {
+#if DIB_PACKED
+  return align_up((size_t)(S > 0 ? S : 0) * box_rounds(n_stride) * (kThreads * 32) * sizeof(Entry<double>), 256);
+#else
+  (void)S; (void)n_stride;
+  return 0;
+#endif
+}
 
 template <typename CT>
 static int launch_boxes(const CT* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, int S, float* table,
-                        cudaStream_t st) {
+                        Entry<CT>* packed, cudaStream_t st) {
   const int rounds_max = box_rounds(n_stride);
   if (rounds_max == 0 || S == 0) return DIB_OK;
   DIB_REQUIRE(S <= 65535, "S (%d) exceeds grid.y; split the batch", S);
   const int groups = rounds_max * kThreads;
   dim3 grid((groups + 7) / 8, S);
-  frustum_boxes_kernel<CT><<<grid, 256, 0, st>>>(xyz, label, n_pts, n_stride, rounds_max, table);
+  frustum_boxes_kernel<CT><<<grid, 256, 0, st>>>(xyz, label, n_pts, n_stride, rounds_max, table, packed);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }
@@ -1740,7 +1798,9 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   // L2), and at least ~2x the resident problems.  Measured on B200 (512 x 60 problems): 1 or 50 samples
   // 103.3 ms, 128 samples 97.7 ms, 256 samples 99.8 ms, 512 samples (no chunking) ~100 ms.
   long long chunk = (2 * grid + a.I - 1) / a.I;
-  const long long bytes_per_sample = (long long)a.n_stride * (3 * (long long)sizeof(CT) + 1);
+  const long long bytes_per_sample =
+      DIB_PACKED ? (long long)a.rounds_max * (kThreads * 32) * (long long)sizeof(Entry<CT>)
+                 : (long long)a.n_stride * (3 * (long long)sizeof(CT) + 1);
   if (bytes_per_sample > 0 && chunk < (32ll << 20) / bytes_per_sample) chunk = (32ll << 20) / bytes_per_sample;
   if (const char* e = getenv("DIB_CHUNK_SAMPLES")) chunk = atoll(e);   // tuning knob
   if (chunk < 1) chunk = 1;
@@ -1786,15 +1846,18 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   off += align_up(n * 4 * sizeof(int32_t), 256);
   float* table = (float*)(ws + off);
   off += box_table_bytes(S, n_stride);
+  Entry<CT>* packed = DIB_PACKED ? (Entry<CT>*)(ws + off) : nullptr;
+  off += packed_bytes(S, n_stride);
   int32_t* perm = (int32_t*)(ws + off);
   a.boxes = table;
+  a.packed = packed;
   a.rounds_max = box_rounds(n_stride);
   a.perm = perm;
   a.xyz = xyz; a.label = label; a.n_pts = n_pts; a.n_stride = n_stride; a.K9 = K9; a.init = init;
   for (int k = 0; k < 3; ++k) { a.lb[k] = lb3[k]; a.ub[k] = ub3[k]; }
   a.H = H; a.W = W; a.max_iter = max_iter; a.S = S; a.I = I;
   DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
-  rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, st);
+  rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, packed, st);
   if (rc != DIB_OK) return rc;
   {
     const int threads = I < 256 ? ((I + 31) / 32) * 32 : 256;
@@ -1824,21 +1887,22 @@ static int evaluate_batch(const CT* xyz, const int8_t* label, const int32_t* n_p
   }
   cudaStream_t st = (cudaStream_t)stream;
   float* table = (float*)workspace;
+  Entry<CT>* packed = DIB_PACKED ? (Entry<CT>*)((unsigned char*)workspace + box_table_bytes(S, n_stride)) : nullptr;
   const int rounds_max = box_rounds(n_stride);
-  rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, st);
+  rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, packed, st);
   if (rc != DIB_OK) return rc;
   if (is_2d) {
     auto kern = frustum_evaluate_kernel<CT, 4>;
     const size_t smem = sizeof(Smem<CT, 4>);
     DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, rounds_max, cost_out, grad_out,
-                                    JtJ_out);
+    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, packed, rounds_max, cost_out,
+                                    grad_out, JtJ_out);
   } else {
     auto kern = frustum_evaluate_kernel<CT, 6>;
     const size_t smem = sizeof(Smem<CT, 6>);
     DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, rounds_max, cost_out, grad_out,
-                                    JtJ_out);
+    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, packed, rounds_max, cost_out,
+                                    grad_out, JtJ_out);
   }
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
@@ -1879,11 +1943,11 @@ size_t frustum_solve_workspace_bytes(int S, int I, int n_stride) {
   const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
   return 256 + dib::align_up(n * 6 * sizeof(double), 256) + dib::align_up(n * sizeof(double), 256) +
          dib::align_up(n * 4 * sizeof(int32_t), 256) + dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0) +
-         dib::align_up(n * sizeof(int32_t), 256);
+         dib::packed_bytes(S, n_stride > 0 ? n_stride : 0) + dib::align_up(n * sizeof(int32_t), 256);
 }
 
 size_t frustum_evaluate_workspace_bytes(int S, int n_stride) {
-  return dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0) + 256;
+  return dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0) + dib::packed_bytes(S, n_stride > 0 ? n_stride : 0) + 256;
 }
 
 int frustum_solve_batch_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
