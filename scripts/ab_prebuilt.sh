@@ -3,10 +3,11 @@
 #   scripts/ab_prebuilt.sh default pipe2 pipe1 ...      ("default" = the in-tree library)
 # Building here instead of on the GPU box keeps nvcc time out of the GPU budget.
 mkdir -p gpurun_out
-for name in "$@"; do
+for item in "$@"; do
+  name="${item%%|*}"; envs=""; [ "$item" != "$name" ] && envs="${item#*|}"     # "variant|ENV=val ENV2=val"
   lib=""; [ "$name" != default ] && lib="deepi2p_b200/lib/variants/$name.so"
-  env DIB_LIB_OVERRIDE="$lib" python bench.py ${BENCH_ARGS:-} --steps 4 --warmup 2 --no-cpu-baseline --samples-per-gpu ${SWEEP_SAMPLES:-512} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err || { echo "RUN FAILED: $name"; tail -3 gpurun_out/sweep_tmp.err; continue; }
-  python - "$name" <<'PY'
+  env DIB_LIB_OVERRIDE="$lib" $envs python bench.py ${BENCH_ARGS:-} --steps 4 --warmup 2 --no-cpu-baseline --samples-per-gpu ${SWEEP_SAMPLES:-512} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err || { echo "RUN FAILED: $name"; tail -3 gpurun_out/sweep_tmp.err; continue; }
+  python - "$item" <<'PY'
 import json, sys
 d = json.load(open("gpurun_out/sweep_tmp.json")); r = d["roofline"]
 print("%-24s reg/s %8.1f  kernel_ms %8.2f %s frac %.3f" % (sys.argv[1], d["value"], r["kernel_ms"], ["%.1f" % v for v in r.get("kernel_ms_all", [])], r["frac"]), flush=True)
