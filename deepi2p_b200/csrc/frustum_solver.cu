@@ -449,8 +449,9 @@ __device__ __noinline__ void make_class(const PoseConst& pc, const Cam& cam, Cla
 
 template <int P>
 __device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab, const ClassConst& cc) {
-  if ((unsigned)lab > 1u) return false;                // labels other than 0/1 carry no residual block
-  if (!cc.enabled) return true;
+  // branch-free on purpose: the DIB_GPS groups of a step are then classified as one straight-line block that
+  // shares the loads of `cc` and interleaves the independent FMA chains
+  const bool lab_ok = (unsigned)lab <= 1u;             // labels other than 0/1 carry no residual block
   const float m = fmaf(cc.G, fabsf(x) + fabsf(y) + fabsf(z), cc.G0);
   float Z, al, ah;
   if (P == 4) {                                        // R = Ry: no y terms in X and Z
@@ -469,7 +470,8 @@ __device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab,
   const bool front = Z > m;
   const bool inside = front && lo4 > m;                    // surely in the image
   const bool outside = (Z < -m) || (front && lo4 < -m);    // surely not
-  return lab == 1 ? !inside : !outside;
+  const bool act = lab == 1 ? !inside : !outside;
+  return lab_ok && (cc.enabled ? act : true);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -988,10 +990,13 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
           const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
           const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
           if (mb[u]) {
+            // one select + one store (the label picks ring, base and mask) instead of two predicated copies
+            const bool l1 = glab[u] != 0;
+            Entry<CT>* ring = l1 ? ring1 : ring0;
+            const int at = (l1 ? head1 + pend1 : head0 + pend0) + __popc((l1 ? m1 : m0) & lt_mask);
             Entry<CT> e;
             e.x = gx[u]; e.y = gy[u]; e.z = gz[u]; e.lab = glab[u];
-            if (glab[u]) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
-            else         ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
+            ring[at & (kRing - 1)] = e;
           }
           pend0 += __popc(m0);
           pend1 += __popc(m1);

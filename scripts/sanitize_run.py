@@ -37,5 +37,7 @@ if which in ("all", "ops"):
     rng = np.random.default_rng(0)
     pts = rng.uniform(0, 10, (2, 3, 3000)).astype(np.float32); nodes = rng.uniform(0, 10, (2, 3, 9)).astype(np.float32)
     print("ball_query_xyz", point_ops.ball_query_xyz_forward(torch.from_numpy(pts).cuda(), torch.from_numpy(nodes).cuda(), 1.5, 12).sum().item())
+    ca = point_ops.cluster_assign_forward(torch.from_numpy(pts).cuda(), torch.from_numpy(nodes).cuda(), 3)
+    print("cluster_assign", ca["count"].sum().item(), ca["pc_decentered"].abs().sum().item())
 torch.cuda.synchronize()
 print("done")
