@@ -533,6 +533,32 @@ template <typename CT> struct Entry;
 template <> struct alignas(16) Entry<float> { float x, y, z; int lab; };
 template <> struct alignas(16) Entry<double> { double x, y, z; long long lab; };
 
+#ifndef DIB_PK_LDG
+#define DIB_PK_LDG 0                          // 1: packed records are read with ld.global.nc (LDG) instead of generic loads
+#endif
+template <typename CT> __device__ __forceinline__ Entry<CT> load_entry(const Entry<CT>* p);
+template <> __device__ __forceinline__ Entry<float> load_entry<float>(const Entry<float>* p) {
+#if DIB_PK_LDG
+  const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+  Entry<float> e;
+  e.x = __int_as_float(v.x); e.y = __int_as_float(v.y); e.z = __int_as_float(v.z); e.lab = v.w;
+  return e;
+#else
+  return *p;
+#endif
+}
+template <> __device__ __forceinline__ Entry<double> load_entry<double>(const Entry<double>* p) {
+#if DIB_PK_LDG
+  const int4 a = __ldg(reinterpret_cast<const int4*>(p)), b = __ldg(reinterpret_cast<const int4*>(p) + 1);
+  Entry<double> e;
+  e.x = __hiloint2double(a.y, a.x); e.y = __hiloint2double(a.w, a.z); e.z = __hiloint2double(b.y, b.x);
+  e.lab = (long long)(((unsigned long long)(unsigned)b.w << 32) | (unsigned)b.z);
+  return e;
+#else
+  return *p;
+#endif
+}
+
 template <typename CT>
 __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict__ xyz,
                                                             const int8_t* __restrict__ label,
@@ -904,7 +930,7 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
             mask &= mask - 1;
             const int i = (r * kThreads + b * kWarps + warp) * 32 + lane;      // this lane's point
 #if DIB_PACKED
-            const Entry<CT> e = pk_s[i];
+            const Entry<CT> e = load_entry<CT>(pk_s + i);
             ll[u] = (int)e.lab; lx[u] = e.x; ly[u] = e.y; lz[u] = e.z;
 #else
             if (i < n) {

@@ -6,14 +6,14 @@ mkdir -p gpurun_out
 python -m pytest tests -m gpu -q 2>&1 | tail -3
 python __graft_entry__.py smoke 2>&1 | tail -1
 python bench.py --steps 5 --warmup 3 --ops > gpurun_out/bench_${tag}.json 2> gpurun_out/bench_${tag}.err
-python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${tag}_reference.json 2>> gpurun_out/bench_${tag}.err
+[ -n "$SKIP_REF" ] || python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${tag}_reference.json 2>> gpurun_out/bench_${tag}.err
 python bench.py --workload single_init --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_${tag}_single_init.json 2>> gpurun_out/bench_${tag}.err
 python bench.py --is-3d --steps 3 --warmup 3 --no-cpu-baseline --samples-per-gpu 256 > gpurun_out/bench_${tag}_6dof.json 2>> gpurun_out/bench_${tag}.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_${tag}.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_launches_${tag}.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:frustum_solve -s 1 -c 1 -o gpurun_out/prof_${tag}_solve \
     python bench.py --samples-per-gpu 512 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_solve_${tag}.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:index_max_kernel\|ball_query_kernel -s 8 -c 2 -o gpurun_out/prof_${tag}_ops \
+[ -n "$SKIP_OPS_NCU" ] || ncu --set full --clock-control none --import-source on -k regex:index_max_kernel\|ball_query_kernel -s 8 -c 2 -o gpurun_out/prof_${tag}_ops \
     python bench.py --ops-only > gpurun_out/ncu_ops_${tag}.log 2>&1
 python - <<PY
 import json
