@@ -660,12 +660,16 @@ struct alignas(16) GroupStage {
 
 template <typename CT, int P>
 struct Smem {
-  alignas(16) float box[kBoxRounds][kBoxRoundFloats];   // bulk-copied (TMA engine) once per problem
+  // Staging buffers of the optional TMA variants shrink to stubs when those variants are compiled out: with
+  // them the CTA needed 23.2 KB and shared memory capped the SM at 9 CTAs although registers allow 10.
+  alignas(16) float box[kBoxRounds][DIB_BOX_SMEM ? kBoxRoundFloats : 4];   // bulk-copied (TMA engine) once per problem
   Entry<CT> list[kWarps][2][kRing];                     // [label 0 | label 1] pending rings
 #if DIB_ACC_SMEM
   double accs[kWarps][NAcc<P>::N][32];                  // per-lane accumulators (column = lane: conflict-free)
 #endif
+#if DIB_GROUP_TMA
   GroupStage<CT> gstage[kWarps][2];                     // double-buffered group staging, private to each warp
+#endif
   alignas(8) uint64_t gbar[kWarps][2];                  // their mbarriers
   alignas(8) uint64_t full;                             // mbarrier of the box-table copy
   double red[kWarps][NAcc<P>::N];
