@@ -389,6 +389,9 @@ def main():
             "workload": "%s: %d KITTI-shaped clouds/GPU x %d pts x %d inits (%s, max_iter 500); N=8 is BASELINE "
                         "config 4" % (args.workload, S_local, n_points, n_inits, "4-DoF" if is_2d else "6-DoF"),
             "samples_per_gpu": S_local, "points": n_points, "inits": n_inits, "parallelism": "dp%d" % world,
+            "why_this_workload": "the per-GPU shard of BASELINE configs[3] (4096 x 20480 x 60 over 8 GPUs), so that "
+                                 "N=1,2,4,8 time the same per-GPU work; configs[1] (4096 x 20480 x 1 init on one GPU) is "
+                                 "--workload single_init (profiles/r01_bench_final_single_init.json), configs[2] is --ops",
             "l2": "L2 flushed (256 MiB write) before every timed step; per-step CUDA events summed",
             "step": "prepare (initial guess + front filter + Philox inits) + LM solve + arg-min"
                     + (" + NCCL all-gather of [S,17] f64" if world > 1 else ""),
