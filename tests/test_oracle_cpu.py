@@ -162,3 +162,34 @@ def test_initial_guess_front_filter():
     assert abs(oracle.wrap_in_pi(iy - smp["ry_gt"])) < 0.6          # heading of the in-frustum points
     assert pf.shape[1] == mask.sum() == lf.shape[0] and mask.sum() < 2000
     assert oracle.wrap_in_pi(3 * math.pi + 0.1) == pytest.approx(-math.pi + 0.1, abs=1e-12)
+
+
+def test_cluster_assign_oracle_matches_reference_formulas():
+    """oracle.cluster_assign against the reference's own torch formulation (models/networks_pc.py:60-82), on CPU:
+    identical indices and counts, means / centres within float tree-sum error."""
+    import torch
+    rng = np.random.default_rng(11)
+    B, N, M, k = 2, 700, 16, 3
+    pc = rng.uniform(-40, 40, (B, 3, N)).astype(np.float32)
+    node = rng.uniform(-40, 40, (B, 3, M)).astype(np.float32)
+    o = oracle.cluster_assign(pc, node, k)
+    p, nd = torch.from_numpy(pc), torch.from_numpy(node)
+    diff = torch.norm(p.unsqueeze(3).expand(B, 3, N, M) - nd.unsqueeze(2).expand(B, 3, N, M), dim=1, p=2)    # :62
+    _, min_k_idx = torch.topk(diff, k=k, dim=2, largest=False, sorted=True)                                    # :63
+    min_idx = min_k_idx[:, :, 0]                                                                               # :64
+    mask = torch.eq(min_idx.unsqueeze(2).expand(B, N, M), torch.arange(M).view(1, 1, M).expand(B, N, M))       # :65-66
+    mask_row_sum = torch.sum(mask.unsqueeze(1).float(), dim=2)                                                 # :70-71
+    cluster_mean = torch.sum(p.unsqueeze(3) * mask.unsqueeze(1).float(), dim=2) / (mask_row_sum + 1e-5)        # :74-75
+    pc_centers = torch.gather(cluster_mean, index=min_idx.unsqueeze(1).expand(B, 3, N), dim=2)                 # :78-80
+    np.testing.assert_array_equal(o["min_k_idx"], min_k_idx.numpy())
+    np.testing.assert_array_equal(o["count"], mask_row_sum[:, 0].numpy().astype(np.int32))
+    np.testing.assert_allclose(o["cluster_mean"], cluster_mean.numpy(), rtol=0, atol=2e-5)
+    np.testing.assert_allclose(o["pc_decentered"], (p - pc_centers).numpy(), rtol=0, atol=2e-5)
+    # exact ties (duplicated node): the oracle's documented rule is "lower node index first"
+    node[:, :, 7] = node[:, :, 3]
+    o = oracle.cluster_assign(pc, node, k)
+    assert not (o["min_k_idx"][:, :, 0] == 7).any()
+    both = (o["min_k_idx"] == 3).any(axis=2) & (o["min_k_idx"] == 7).any(axis=2)
+    pos3 = np.argmax(o["min_k_idx"] == 3, axis=2)
+    pos7 = np.argmax(o["min_k_idx"] == 7, axis=2)
+    assert (pos3[both] < pos7[both]).all()
