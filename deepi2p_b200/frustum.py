@@ -86,8 +86,10 @@ def _as_K(K, S, device):
 _ws_cache = {}
 
 
-def _workspace(nbytes, device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+def _workspace(nbytes, device, stream_ptr=0):
+    """Scratch buffer of the solver, cached per (device, stream): launches on different streams may overlap, so
+    they must not share a workspace; launches on one stream are ordered and can."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), int(stream_ptr))
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
@@ -146,11 +148,12 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
                 costs = torch.empty((S, I), dtype=torch.float64, device=dev)
                 stats = torch.empty((S, I, 4), dtype=torch.int32, device=dev)
         wsb = lib.frustum_solve_workspace_bytes(S, I, Ns)
-        ws = _workspace(wsb, dev)
+        sp = _stream_ptr(stream)
+        ws = _workspace(wsb, dev, sp)
         fn = lib.frustum_solve_batch_f32 if xyz.dtype == torch.float32 else lib.frustum_solve_batch_f64
         rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(init), lb.ctypes.data, ub.ctypes.data,
                 float(H), float(W), int(max_iter), 1 if is_2d else 0, S, I, _ptr(P), _ptr(cost), _ptr(best),
-                _ptr(params), _ptr(costs), _ptr(stats), _ptr(ws), ws.numel(), _stream_ptr(stream))
+                _ptr(params), _ptr(costs), _ptr(stats), _ptr(ws), ws.numel(), sp)
     _native.check(rc, "frustum_solve_batch")
     res = dict(P=P, cost=cost, best=best)
     if return_all:
@@ -170,10 +173,11 @@ def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None):
         cost = torch.empty((S,), dtype=torch.float64, device=dev)
         grad = torch.empty((S, 6), dtype=torch.float64, device=dev)
         JtJ = torch.empty((S, 36), dtype=torch.float64, device=dev)
-        ws = _workspace(lib.frustum_evaluate_workspace_bytes(S, Ns), dev)
+        sp = _stream_ptr(stream)
+        ws = _workspace(lib.frustum_evaluate_workspace_bytes(S, Ns), dev, sp)
         fn = lib.frustum_evaluate_f32 if xyz.dtype == torch.float32 else lib.frustum_evaluate_f64
         rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(x), float(H), float(W), 1 if is_2d else 0, S,
-                _ptr(cost), _ptr(grad), _ptr(JtJ), _ptr(ws), ws.numel(), _stream_ptr(stream))
+                _ptr(cost), _ptr(grad), _ptr(JtJ), _ptr(ws), ws.numel(), sp)
     _native.check(rc, "frustum_evaluate")
     P = 4 if is_2d else 6
     return cost, grad[:, :P], JtJ[:, :P * P].reshape(S, P, P)

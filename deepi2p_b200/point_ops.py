@@ -75,10 +75,11 @@ def ball_query_xyz_forward(points, nodes, radius, K):
     dev = points.device
     with torch.cuda.device(dev):
         need = lib.ball_query_xyz_workspace_bytes(B, N)
-        ws = _xyz_ws.get(dev.index)
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)     # one scratch per stream: launches may overlap
+        ws = _xyz_ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=dev)
-            _xyz_ws[dev.index] = ws
+            _xyz_ws[key] = ws
         out = torch.empty((B, M, K), dtype=torch.int32, device=dev)
         rc = lib.ball_query_xyz_forward(points.data_ptr(), nodes.data_ptr(), float(radius), out.data_ptr(), B, M, N, K,
                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream)
@@ -107,10 +108,11 @@ def cluster_assign_forward(pc, node, k=1, want_centers=True):
     dev = pc.device
     with torch.cuda.device(dev):
         need = lib.cluster_assign_workspace_bytes(B, M)
-        ws = _ca_ws.get(dev.index)
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        ws = _ca_ws.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(max(need, 1 << 16), dtype=torch.uint8, device=dev)
-            _ca_ws[dev.index] = ws
+            _ca_ws[key] = ws
         topk = torch.empty((B, N, k), dtype=torch.int32, device=dev)
         min_idx = torch.empty((B, N), dtype=torch.int32, device=dev)
         count = torch.empty((B, M), dtype=torch.int32, device=dev)
