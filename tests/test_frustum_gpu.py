@@ -456,3 +456,36 @@ def test_register_directory_legacy_handoff(cuda, tmp_path):
         assert abs(t - res["t_err"][s]) < 1e-9 and abs(r - res["r_err"][s]) < 1e-7
     sm = res["summary"]
     assert sm["n"] == S and 0.0 <= sm["success_rate"] <= 1.0 and np.isfinite(sm["rte_mean"])
+
+
+@pytest.mark.parametrize("is_2d", [True, False])
+def test_committed_golden_vectors(cuda, is_2d):
+    """CUDA path against tests/golden/frustum_small.npz (oracle outputs committed with their generating script):
+    evaluations to the same tolerance as test_evaluate_matches_oracle, solves statistically (see
+    test_solve_matches_oracle for why)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frustum_small.npz"))
+    S, I, H, W = int(g["S"]), int(g["I"]), float(g["H"]), float(g["W"])
+    P = 4 if is_2d else 6
+    xyz, lab, n_pts = frustum.pack_clouds(g["points"], g["pred"])
+    K = g["K"].reshape(S, 9)
+    x = np.zeros((S, 6))
+    x[:, :P] = g["x4"] if is_2d else g["x6"]
+    c, gr, A = frustum.evaluate_batch(xyz, lab, n_pts, K, x, H, W, is_2d)
+    ev = g["eval4"] if is_2d else g["eval6"]
+    for s in range(S):
+        co, go, Ao = ev[s, 0], ev[s, 1:1 + P], ev[s, 1 + P:].reshape(P, P)
+        assert abs(c[s].item() - co) <= 1e-10 * max(1.0, abs(co))
+        np.testing.assert_allclose(gr[s].cpu().numpy(), go, rtol=1e-9, atol=1e-9 * np.abs(go).max())
+        np.testing.assert_allclose(A[s].cpu().numpy(), Ao, rtol=1e-9, atol=1e-9 * np.abs(Ao).max())
+    out = frustum.solve_batch(xyz, lab, n_pts, K, g["inits"], H, W, syn.T_LB, syn.T_UB, 500, is_2d, return_all=True)
+    params = out["params"].cpu().numpy()
+    sol = g["solve4"] if is_2d else g["solve6"]
+    nr = P - 3
+    d_rot = np.linalg.norm(params[:, :, :nr] - sol[:, :, :nr], axis=2)
+    d_tr = np.linalg.norm(params[:, :, nr:P] - sol[:, :, nr:P], axis=2)
+    within = (d_rot < ROT_TOL) & (d_tr < TRANS_TOL)
+    print("golden solves within gate %d/%d" % (within.sum(), within.size))
+    assert within.sum() >= 0.75 * within.size
+    costs = out["costs"].cpu().numpy()
+    assert np.all(np.abs(costs[within] - sol[:, :, 6][within]) <= 1e-5 * np.maximum(1.0, sol[:, :, 6][within]))

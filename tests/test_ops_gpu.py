@@ -244,3 +244,13 @@ def test_cluster_assign_argument_checks(cuda):
         point_ops.cluster_assign_forward(p.cpu(), nd, 1)
     out = point_ops.cluster_assign_forward(torch.zeros(2, 3, 0, device="cuda"), torch.ones(2, 3, 4, device="cuda"), 2)
     assert out["min_k_idx"].shape == (2, 0, 2) and (out["count"] == 0).all() and (out["cluster_mean"] == 0).all()
+
+
+def test_cluster_assign_committed_golden(cuda):
+    g = np.load(os.path.join(GOLDEN, "frustum_small.npz")) if "GOLDEN" in globals() else np.load(
+        os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frustum_small.npz"))
+    got = point_ops.cluster_assign_forward(torch.from_numpy(g["ca_pc"]).cuda(), torch.from_numpy(g["ca_node"]).cuda(), 3)
+    np.testing.assert_array_equal(got["min_k_idx"].cpu().numpy(), g["ca_min_k_idx"])
+    np.testing.assert_array_equal(got["count"].cpu().numpy(), g["ca_count"])
+    np.testing.assert_array_equal(got["cluster_mean"].cpu().numpy(), g["ca_mean"])
+    np.testing.assert_array_equal(got["pc_decentered"].cpu().numpy(), g["ca_decentered"])

@@ -193,3 +193,30 @@ def test_cluster_assign_oracle_matches_reference_formulas():
     pos3 = np.argmax(o["min_k_idx"] == 3, axis=2)
     pos7 = np.argmax(o["min_k_idx"] == 7, axis=2)
     assert (pos3[both] < pos7[both]).all()
+
+
+def test_oracle_reproduces_committed_golden_vectors():
+    """tests/golden/frustum_small.npz (tests/golden/make_frustum_golden.py): the oracle must keep producing the
+    vectors the GPU parity tests are also checked against."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "frustum_small.npz"))
+    S, I, H, W = int(g["S"]), int(g["I"]), float(g["H"]), float(g["W"])
+    for s in range(S):
+        pts, pred, K = g["points"][s].astype(np.float64), g["pred"][s], g["K"][s]
+        for is_2d, x, ev, sol in ((True, g["x4"][s], g["eval4"][s], g["solve4"][s]),
+                                  (False, g["x6"][s], g["eval6"][s], g["solve6"][s])):
+            P = 4 if is_2d else 6
+            c, gr, A = oracle.evaluate(pts, pred, K, x, H, W, is_2d)
+            np.testing.assert_allclose(np.concatenate([[c], gr, A.reshape(-1)]), ev, rtol=1e-12, atol=1e-12)
+            ms = oracle.solve_multistart(pts, pred, K, g["inits"][s][:, 0], g["inits"][s][:, 1:4], H, W,
+                                         (-5.0, -0.1, -10.0), (5.0, 0.1, 10.0), 500, is_2d)
+            np.testing.assert_allclose(ms["params"][:, :P], sol[:, :P], rtol=0, atol=1e-9)
+            np.testing.assert_allclose(ms["costs"], sol[:, 6], rtol=1e-9)
+            for i in range(I):
+                st = ms["stats"][i]
+                assert [st["iterations"], st["unique_evals"], st["termination"]] == sol[i, 7:10].astype(int).tolist()
+    ca = oracle.cluster_assign(g["ca_pc"], g["ca_node"], 3)
+    np.testing.assert_array_equal(ca["min_k_idx"], g["ca_min_k_idx"])
+    np.testing.assert_array_equal(ca["count"], g["ca_count"])
+    np.testing.assert_array_equal(ca["cluster_mean"], g["ca_mean"])
+    np.testing.assert_array_equal(ca["pc_decentered"], g["ca_decentered"])
