@@ -86,3 +86,21 @@ def test_pack_clouds_layout_and_precision_choice():
     pts2 = pts + 1e-9
     xyz2, _, _ = frustum.pack_clouds(pts2, lab, device="cpu")
     assert str(xyz2.dtype) == "torch.float64"
+
+
+def test_header_is_plain_c_and_cluster_assign_validates_on_host(tmp_path):
+    """The boundary must be bindable from C / cgo / JNI: the header has to compile as C11 without CUDA headers."""
+    import subprocess
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "deepi2p_b200.h"\n'
+                   'int probe(void) { return dib_abi_version() + (int)frustum_solve_workspace_bytes(1, 1, 16); }\n')
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           str(src)])
+    from deepi2p_b200 import _native
+    lib = _native.load()
+    buf = ctypes.create_string_buffer(256)
+    a = ctypes.addressof(buf)
+    assert lib.cluster_assign_forward(a, a, 1, 4, 2, 3, a, a, a, a, None, None, a, 256, None) == -22     # k > M
+    assert b"k" in lib.dib_last_error()
+    assert lib.cluster_assign_forward(a, a, 1, 4, 4000, 1, a, a, a, a, None, None, a, 256, None) == -22  # M > 2048
+    assert lib.cluster_assign_workspace_bytes(8, 128) == 8 * 3 * 128 * 8
