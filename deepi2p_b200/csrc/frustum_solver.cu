@@ -4,8 +4,9 @@
 // Replaces FrustumRegistration.solvePGivenK (evaluation/frustum_reg/src/registration.cpp:9-186)
 // and the multi-start loop around it (evaluation/registration_lsq.py:127-186).  One thread block
 // owns one (cloud, labels, intrinsics, init pose) problem from its first evaluation to its final
-// pose: point tiles are staged into shared memory with 1-D bulk copies (TMA engine) signalled on
-// mbarriers, every thread evaluates the per-point residual / Jacobian in fp64, the block reduces
+// pose: per pass the block culls whole 32-point groups against the frustum with a per-launch box table,
+// classifies the points of undecided groups in fp32 with a conservative margin, evaluates the
+// maybe-active ones exactly in fp64 (residual, analytic Jacobian, Cauchy corrector), reduces
 // cost, J^T r and J^T J in a fixed order, and thread 0 runs the trust-region control flow
 // (Jacobi scaling, LM damping, Cholesky of the damped normal matrix, model cost change, box
 // projection, projected Armijo line search with cubic interpolation, step acceptance and the
@@ -23,6 +24,10 @@
 
 namespace dib {
 
+#ifndef DIB_WIDE_TU
+#define DIB_WIDE_TU 0                         // 1: this file is being compiled a second time by frustum_solver_wide.cu (128-thread
+#endif                                        //    CTAs, own namespace); the C ABI and the error buffer live in the primary TU only
+#if !DIB_WIDE_TU
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -30,6 +35,7 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+#endif
 
 #ifndef DIB_THREADS
 #define DIB_THREADS 64
@@ -1962,7 +1968,61 @@ static int residuals_single(const CT* xyz, const int8_t* label, int n, int n_str
   return DIB_OK;
 }
 
+static size_t solve_workspace_bytes_impl(int S, int I, int n_stride) {
+  const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
+  return 256 + align_up(n * 6 * sizeof(double), 256) + align_up(n * sizeof(double), 256) +
+         align_up(n * 4 * sizeof(int32_t), 256) + box_table_bytes(S, n_stride > 0 ? n_stride : 0) +
+         packed_bytes(S, n_stride > 0 ? n_stride : 0) + align_up(n * sizeof(int32_t), 256);
+}
+
+#if DIB_WIDE_TU
+// Entry points of the wide (128-thread CTA) build of this file; called by the primary TU's C ABI for
+// batches with few problems (a problem then finishes ~1.8x sooner and the persistent grid balances better).
+size_t wide_solve_workspace_bytes(int S, int I, int n_stride) { return solve_workspace_bytes_impl(S, I, n_stride); }
+int wide_solve_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
+                   const double* init, const double* lb3, const double* ub3, double H, double W, int max_iter, int is_2d,
+                   int S, int I, double* P16_out, double* cost_out, int32_t* best_out, double* params_all,
+                   double* cost_all, int32_t* stats_all, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+  return solve_batch<float>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
+                            cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
+}
+int wide_solve_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
+                   const double* init, const double* lb3, const double* ub3, double H, double W, int max_iter, int is_2d,
+                   int S, int I, double* P16_out, double* cost_out, int32_t* best_out, double* params_all,
+                   double* cost_all, int32_t* stats_all, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+  return solve_batch<double>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
+                             cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
+}
+#endif
+
 }  // namespace dib
+
+#if !DIB_WIDE_TU
+#ifndef DIB_HAVE_WIDE
+#define DIB_HAVE_WIDE 0                       // set by the build when frustum_solver_wide.cu is linked in
+#endif
+#if DIB_HAVE_WIDE
+namespace dib_w128 {
+size_t wide_solve_workspace_bytes(int S, int I, int n_stride);
+int wide_solve_f32(const float*, const int8_t*, const int32_t*, int, const double*, const double*, const double*,
+                   const double*, double, double, int, int, int, int, double*, double*, int32_t*, double*, double*,
+                   int32_t*, void*, size_t, dib_stream_t);
+int wide_solve_f64(const double*, const int8_t*, const int32_t*, int, const double*, const double*, const double*,
+                   const double*, double, double, int, int, int, int, double*, double*, int32_t*, double*, double*,
+                   int32_t*, void*, size_t, dib_stream_t);
+}  // namespace dib_w128
+#endif
+// Batches with fewer than DIB_WIDE_BELOW problems (S x I) go to the 128-thread build.  Experimental: the
+// default 0 never does (not yet measured on a B200; scripts/round2_sweep.sh).
+static bool use_wide(int S, int I) {
+#if DIB_HAVE_WIDE
+  static const long long below = getenv("DIB_WIDE_BELOW") ? atoll(getenv("DIB_WIDE_BELOW")) : 0;
+  return (long long)S * I < below;
+#else
+  (void)S; (void)I;
+  return false;
+#endif
+}
 
 extern "C" {
 
@@ -1977,10 +2037,12 @@ int dib_device_sm_count(void) {
 }
 
 size_t frustum_solve_workspace_bytes(int S, int I, int n_stride) {
-  const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
-  return 256 + dib::align_up(n * 6 * sizeof(double), 256) + dib::align_up(n * sizeof(double), 256) +
-         dib::align_up(n * 4 * sizeof(int32_t), 256) + dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0) +
-         dib::packed_bytes(S, n_stride > 0 ? n_stride : 0) + dib::align_up(n * sizeof(int32_t), 256);
+  size_t need = dib::solve_workspace_bytes_impl(S, I, n_stride);
+#if DIB_HAVE_WIDE
+  const size_t wide = dib_w128::wide_solve_workspace_bytes(S, I, n_stride);
+  if (wide > need) need = wide;
+#endif
+  return need;
 }
 
 size_t frustum_evaluate_workspace_bytes(int S, int n_stride) {
@@ -1992,6 +2054,11 @@ int frustum_solve_batch_f32(const float* xyz, const int8_t* label, const int32_t
                             double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
                             int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
                             void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+#if DIB_HAVE_WIDE
+  if (use_wide(S, I))
+    return dib_w128::wide_solve_f32(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
+                                    cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
+#endif
   return dib::solve_batch<float>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
                                  P16_out, cost_out, best_out, params_all, cost_all, stats_all, workspace,
                                  workspace_bytes, stream);
@@ -2002,6 +2069,11 @@ int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_
                             double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
                             int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
                             void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+#if DIB_HAVE_WIDE
+  if (use_wide(S, I))
+    return dib_w128::wide_solve_f64(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
+                                    cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
+#endif
   return dib::solve_batch<double>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
                                   P16_out, cost_out, best_out, params_all, cost_all, stats_all, workspace,
                                   workspace_bytes, stream);
@@ -2033,3 +2105,4 @@ int frustum_residuals_f64(const double* xyz, const int8_t* label, int n, int n_s
 }
 
 }  // extern "C"
+#endif  // !DIB_WIDE_TU

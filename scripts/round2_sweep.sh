@@ -27,7 +27,9 @@ case "${1:-}" in
     names=(default); for v in "${variants[@]}"; do names+=("${v%%|*}"); done; names+=(default)
     scripts/ab_prebuilt.sh "${names[@]}"
     echo "--- config 2 (4096 x 1 init): CTA width"
-    BENCH_ARGS="--workload single_init" SWEEP_SAMPLES=4096 scripts/ab_prebuilt.sh default t128x5 t32x20
+    BENCH_ARGS="--workload single_init" SWEEP_SAMPLES=4096 scripts/ab_prebuilt.sh default "default|DIB_WIDE_BELOW=1000000" t128x5 t32x20
+    echo "--- the in-library 128-thread build (frustum_solver_wide.cu) through the whole parity suite"
+    DIB_WIDE_BELOW=1000000000 python -m pytest tests/test_frustum_gpu.py -m gpu -q 2>&1 | tail -3
     echo "--- overlapped steps"
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --streams 2 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('streams=2 value', d['value'], 'e2e', d['e2e']['value'])"
     ;;
