@@ -15,6 +15,8 @@ variants=(
   "t128x5|-DDIB_THREADS=128 -DDIB_MINBLOCKS4=5 -DDIB_MINBLOCKS6=4"
   "gps3|-DDIB_GPS=3"
   "ilp2|-DDIB_EXACT_ILP=2 -DDIB_MINBLOCKS4=8"
+  "six9|-DDIB_MINBLOCKS6=9 -DDIB_RING=64 -DDIB_GPS=1"
+  "six10|-DDIB_MINBLOCKS6=10 -DDIB_RING=64 -DDIB_GPS=1"
 )
 case "${1:-}" in
   build)
@@ -30,6 +32,8 @@ case "${1:-}" in
     BENCH_ARGS="--workload single_init" SWEEP_SAMPLES=4096 scripts/ab_prebuilt.sh default "default|DIB_WIDE_BELOW=1000000" t128x5 t32x20
     echo "--- the in-library 128-thread build (frustum_solver_wide.cu) through the whole parity suite"
     DIB_WIDE_BELOW=1000000000 python -m pytest tests/test_frustum_gpu.py -m gpu -q 2>&1 | tail -3
+    echo "--- 6-DoF occupancy (96 registers, smaller rings: 9-10 CTAs/SM instead of 8)"
+    BENCH_ARGS="--is-3d" SWEEP_SAMPLES=256 scripts/ab_prebuilt.sh default six9 six10 default
     echo "--- overlapped steps"
     python bench.py --steps 6 --warmup 3 --no-cpu-baseline --streams 2 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('streams=2 value', d['value'], 'e2e', d['e2e']['value'])"
     ;;
