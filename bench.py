@@ -494,7 +494,7 @@ def main():
             "registrations_gpu_cost_le_oracle": cost_le,
             "best_of_I_max_rot_err_rad": worst_r, "best_of_I_max_trans_err_m": worst_t,
             "note": "trajectories are chaotic at rounding level: the CPU oracle against itself with an equivalent "
-                    "linear solver differs in ~3-4 % of solves (scripts/parity_sensitivity_cpu.py)"}
+                    "linear solver differs in ~3-4 % of solves (tests/tools/parity_sensitivity_cpu.py)"}
 
     if args.ops:
         line["ops"] = bench_ops(torch, dev, peak)

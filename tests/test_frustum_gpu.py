@@ -77,7 +77,7 @@ def test_solve_matches_oracle(cuda, is_2d):
     """Trajectory-level parity.  The objective is piecewise smooth with thousands of kinks and the
     solver stops on a 1e-6 relative function tolerance, so trajectories are chaotic at the rounding
     level: even the CPU oracle against itself with an algebraically equivalent linear solver moves
-    ~3-4 % of full-size solves by > 1e-7 (scripts/parity_sensitivity_cpu.py).  The gate is therefore
+    ~3-4 % of full-size solves by > 1e-7 (tests/tools/parity_sensitivity_cpu.py).  The gate is therefore
     statistical: at least 90 % of the (sample, init) solves within 1e-4 rad / 1e-3 m of the oracle
     with identical iteration / evaluation counts, and a tiny median difference."""
     S, I, n = 6, 5, 4096

@@ -1,7 +1,7 @@
 """Find (sample, init) solves where the GPU and the CPU oracle disagree, and localise the cause."""
 import sys, os, math
 import numpy as np, torch
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from concurrent.futures import ThreadPoolExecutor
 from deepi2p_b200 import frustum, synthetic as syn

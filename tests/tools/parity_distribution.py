@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """GPU vs CPU-oracle parity distribution over many full-size solves (run on the GPU box):
-    python scripts/parity_distribution.py [n_samples] [6dof] > gpurun_out/parity_distribution.json"""
+    python tests/tools/parity_distribution.py [n_samples] [6dof] > gpurun_out/parity_distribution.json"""
 import json, os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import oracle
 from concurrent.futures import ThreadPoolExecutor
 from deepi2p_b200 import frustum, synthetic as syn

@@ -10,7 +10,7 @@ by > 1e-7 (2 beyond 1e-4, max 0.74); QR vs Cholesky(long double) 4/120 differ by
 1.4e-4).  So even an algebraically equivalent, more accurate solver changes ~3-4 % of the
 trajectories: pose parity between any two implementations is statistical, not exact.
 
-    python scripts/parity_sensitivity_cpu.py [n_samples]
+    python tests/tools/parity_sensitivity_cpu.py [n_samples]
 """
 import ctypes
 import os
@@ -20,7 +20,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 PATCH_OLD = "    bool ok = householder_lstsq(A, b, m + P, P, y);"
