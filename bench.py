@@ -82,6 +82,21 @@ def load_traffic(S_local, n_inits, is_2d):
     return None
 
 
+def load_ncu_fractions(S_local, n_inits, is_2d):
+    """FP64-pipe and issue-slot utilisation of the dominant kernel from the same committed ncu capture (SURVEY 8d asks
+    for the FP64-ALU fraction next to the bandwidth fraction); None when the capture is of another workload."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    try:
+        with open(p) as f:
+            t = json.load(f)
+        if t["samples_per_gpu"] == S_local and t["inits"] == n_inits and bool(t["is_2d"]) == bool(is_2d):
+            return {"fp64_pipe_active_pct": t.get("fp64_pipe_active_pct"), "issue_active_pct": t.get("issue_active_pct"),
+                    "source": "profiles/r01_traffic.json (%s)" % t.get("source")}
+    except Exception:  # noqa: BLE001
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  nvidia-smi needs a few hundred ms to
     start emitting, so the sampler is started before the warm-up and the samples are filtered to the timed
@@ -448,6 +463,7 @@ def main():
             "mean_lm_iterations_per_solve": float(stats[:, :, 0].mean().item()),
             "compulsory_bytes_per_launch": compulsory,
             "traffic": load_traffic(S_local, n_inits, is_2d),
+            "ncu": load_ncu_fractions(S_local, n_inits, is_2d),
             "note": "algorithmic = 13 B x points x cloud passes the solver performed (streamed model, SURVEY 8d); the "
                     "cloud is re-read from L2/shared memory, so DRAM traffic (profiles/) is far below it",
         },

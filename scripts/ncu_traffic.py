@@ -14,6 +14,16 @@ out = {"kernel": vals[hdr.index("Kernel Name")], "samples_per_gpu": S, "inits": 
        "lts_t_bytes": get("lts__t_bytes.sum") if "lts__t_bytes.sum" in hdr else None,
        "gpu_time_ns": float(vals[hdr.index("gpu__time_duration.sum")].replace(",", "")) * {"ns": 1, "us": 1e3, "ms": 1e6, "s": 1e9}[units[hdr.index("gpu__time_duration.sum")]],
        "source": os.path.basename(rep)}
+def pct(name):
+    try:
+        return float(vals[hdr.index(name)].replace(",", ""))
+    except (ValueError, IndexError):
+        return None
+# the FP64-ALU fraction is reported next to the bandwidth fraction
+out["fp64_pipe_active_pct"] = pct("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
+out["issue_active_pct"] = pct("smsp__issue_active.avg.pct_of_peak_sustained_active")
+out["registers_per_thread"] = pct("launch__registers_per_thread")
+out["grid_size"] = pct("launch__grid_size")
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 json.dump(out, open(os.path.join(root, "profiles", "r01_traffic.json"), "w"), indent=1)
 print(out)
