@@ -65,8 +65,11 @@ int dib_device_sm_count(void);
  *                                 contractions, termination code)
  * Termination codes: 0 gradient tol, 1 parameter tol, 2 function tol, 3 max iterations,
  *   4 min trust-region radius, 5 too many invalid steps, 6 infeasible start (init returned).
- * workspace: [dev] scratch of at least frustum_solve_workspace_bytes(S, I, n_stride) bytes (per-problem
- *   results + the per-group bounding-box table the solver builds from the cloud at every call).
+ * workspace: [dev] 256-byte aligned scratch of at least frustum_solve_workspace_bytes(S, I, n_stride) bytes:
+ *   per-problem results, the per-group bounding-box table (1 B/point) and the packed {x,y,z,label} copy of the
+ *   clouds (sized for the f64 record: 32 B/point) that the solver builds from the cloud at every call, i.e.
+ *   about 35 B per point of the batch (366 MB for 512 clouds x 20480 points).  Calls that may overlap on
+ *   different streams need separate workspaces.
  * ------------------------------------------------------------------------------------------ */
 size_t frustum_solve_workspace_bytes(int S, int I, int n_stride);
 
