@@ -418,6 +418,9 @@ def main():
         e1.record(); e1.synchronize()
         k_all.append(e0.elapsed_time(e1))
     k_ms = sum(k_all) / reps
+    tl = frustum.last_solve_timeline(dev)
+    tail_ms = (tl[2] - tl[1]) * 1e-6 if tl else None
+    span_ms = (tl[2] - tl[0]) * 1e-6 if tl else None
     stats = res["stats"].to(torch.float64)
     passes = stats[:, :, 1]
     pts_evals = float((passes * prep["n_pts"].to(torch.float64)[:, None]).sum().item())
@@ -458,7 +461,7 @@ def main():
             "bound": "hbm", "kernel": "frustum_solve_kernel<float,%d>" % (4 if is_2d else 6),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernel_ms_all": k_all,
-            "point_evals_per_s": pts_evals / (k_ms * 1e-3),
+            "point_evals_per_s": pts_evals / (k_ms * 1e-3), "tail_ms": tail_ms, "kernel_span_ms": span_ms,
             "mean_cloud_passes_per_solve": float(passes.mean().item()),
             "mean_lm_iterations_per_solve": float(stats[:, :, 0].mean().item()),
             "compulsory_bytes_per_launch": compulsory,

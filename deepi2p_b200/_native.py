@@ -11,8 +11,9 @@ _c = ctypes
 _lib = None
 
 EXPORTS = (
-    "dib_abi_version", "dib_last_error", "dib_device_sm_count",
-    "frustum_solve_workspace_bytes", "frustum_solve_batch_f32", "frustum_solve_batch_f64",
+    "dib_abi_version", "dib_last_error", "dib_device_sm_count", "dib_profile_solve_events",
+    "frustum_solve_workspace_bytes", "frustum_solve_batch_f32", "frustum_solve_batch_f64", "frustum_solve_traced_f32",
+    "frustum_register_workspace_bytes", "frustum_register_batch_f32",
     "frustum_evaluate_workspace_bytes",
     "frustum_evaluate_f32", "frustum_evaluate_f64", "frustum_residuals_f32", "frustum_residuals_f64",
     "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32",
@@ -20,6 +21,9 @@ EXPORTS = (
     "index_max_forward", "ball_query_forward", "ball_query_xyz_workspace_bytes", "ball_query_xyz_forward",
     "cluster_assign_workspace_bytes", "cluster_assign_forward",
 )
+
+
+EXPECTED_ABI = 3        # dib_abi_version() the argtypes below were written for
 
 
 class NativeError(RuntimeError):
@@ -49,11 +53,20 @@ def load():
                 raise NativeError(
                     f"deepi2p_b200 CUDA library is missing ({path}) and could not be built: {e}. "
                     "There is no CPU fallback; run `python -m deepi2p_b200.build`.") from e
+            import warnings
+            warnings.warn(f"deepi2p_b200: {path} is older than its sources and the rebuild failed ({e}); "
+                          "loading the stale library (its ABI version is checked)")
     lib = ctypes.CDLL(path)
     vp, i32, f64, sz = _c.c_void_p, _c.c_int, _c.c_double, _c.c_size_t
     lib.dib_abi_version.restype = i32
+    abi = lib.dib_abi_version()
+    if abi != EXPECTED_ABI:
+        raise NativeError(f"{path} has ABI version {abi}, this binding was written for {EXPECTED_ABI}: "
+                          "rebuild with `python -m deepi2p_b200.build --force`")
     lib.dib_last_error.restype = _c.c_char_p
     lib.dib_device_sm_count.restype = i32
+    lib.dib_profile_solve_events.restype = None
+    lib.dib_profile_solve_events.argtypes = [vp, vp]
     lib.frustum_solve_workspace_bytes.restype = sz
     lib.frustum_solve_workspace_bytes.argtypes = [i32, i32, i32]
     lib.frustum_evaluate_workspace_bytes.restype = sz
@@ -63,6 +76,13 @@ def load():
     for name in ("frustum_solve_batch_f32", "frustum_solve_batch_f64"):
         getattr(lib, name).restype = i32
         getattr(lib, name).argtypes = solve_args
+    lib.frustum_solve_traced_f32.restype = i32
+    lib.frustum_solve_traced_f32.argtypes = solve_args[:20] + [vp, i32] + solve_args[20:]
+    lib.frustum_register_workspace_bytes.restype = sz
+    lib.frustum_register_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.frustum_register_batch_f32.restype = i32
+    lib.frustum_register_batch_f32.argtypes = [vp, vp, i32, i32, i32, i32, _c.c_uint64, f64, f64, vp, vp, vp, f64, f64,
+                                               i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
     eval_args = [vp, vp, vp, i32, vp, vp, f64, f64, i32, i32, vp, vp, vp, vp, sz, vp]
     for name in ("frustum_evaluate_f32", "frustum_evaluate_f64"):
         getattr(lib, name).restype = i32

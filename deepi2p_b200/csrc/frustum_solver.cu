@@ -2,16 +2,25 @@
 // ("frustum") registration problem, written for sm_100a.
 //
 // Replaces FrustumRegistration.solvePGivenK (evaluation/frustum_reg/src/registration.cpp:9-186)
-// and the multi-start loop around it (evaluation/registration_lsq.py:127-186).  One thread block
-// owns one (cloud, labels, intrinsics, init pose) problem from its first evaluation to its final
-// pose: per pass the block culls whole 32-point groups against the frustum with a per-launch box table,
+// and the multi-start loop around it (evaluation/registration_lsq.py:127-186).
+//
+// Execution model (round 2): ONE WARP owns one (cloud, labels, intrinsics, init pose) problem from its
+// first evaluation to its final pose; a CTA is a team of warps (one CTA per SM) that share nothing in the
+// steady state -- there is no CTA-wide barrier anywhere in the solve loop.  A pass over the cloud is cut
+// into a FIXED sequence of slices (a few rounds of 32 groups x 32 points each); each slice is reduced on
+// its own, in a fixed order, and the slice sums are added in slice order.  Because a slice's sum does not
+// depend on which warp computed it, warps that have run out of problems (the end-of-kernel tail, small
+// batches, the single-problem drop-in call) claim open slices of their CTA-mates' passes through shared
+// memory and the results stay bit-identical run to run and independent of who helped.
+//
+// Per slice a warp culls whole 32-point groups against the frustum with a per-launch box table,
 // classifies the points of undecided groups in fp32 with a conservative margin, evaluates the
-// maybe-active ones exactly in fp64 (residual, analytic Jacobian, Cauchy corrector), reduces
-// cost, J^T r and J^T J in a fixed order, and thread 0 runs the trust-region control flow
-// (Jacobi scaling, LM damping, Cholesky of the damped normal matrix, model cost change, box
-// projection, projected Armijo line search with cubic interpolation, step acceptance and the
-// tolerance tests) without ever returning to the host.  A persistent grid pulls problems from an
-// atomic queue; a second tiny kernel takes the per-sample arg-min over inits and builds the 4x4.
+// maybe-active ones exactly in fp64 (residual, analytic Jacobian, Cauchy corrector) and reduces cost,
+// J^T r and J^T J; lane 0 of the owning warp runs the trust-region control flow (Jacobi scaling, LM
+// damping, Cholesky of the damped normal matrix, model cost change, box projection, projected Armijo
+// line search with cubic interpolation, step acceptance and the tolerance tests) without ever returning
+// to the host.  A persistent grid pulls problems from an atomic queue; a second tiny kernel takes the
+// per-sample arg-min over inits and builds the 4x4.
 //
 // Residual definitions: registration_3d.hpp:34-68,105-127 / registration_2d.hpp:34-69,106-129.
 // Algorithm text: SURVEY.md Appendix A; oracle/frustum_oracle.cpp is the CPU checker.
@@ -24,10 +33,6 @@
 
 namespace dib {
 
-#ifndef DIB_WIDE_TU
-#define DIB_WIDE_TU 0                         // 1: this file is being compiled a second time by frustum_solver_wide.cu (128-thread
-#endif                                        //    CTAs, own namespace); the C ABI and the error buffer live in the primary TU only
-#if !DIB_WIDE_TU
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -35,21 +40,30 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
-#endif
 
-#ifndef DIB_THREADS
-#define DIB_THREADS 64
+// Warps per CTA (= problems in flight per SM; one CTA per SM).  The register budget decides: 20 warps x 32
+// lanes x 96 registers for the 4-DoF solver, fewer for 6-DoF (128 registers) and for the f64 record (rings
+// twice as large); shared memory (rings + accumulators + per-problem state) is checked below.
+#ifndef DIB_WARPS_F4
+#define DIB_WARPS_F4 20
 #endif
-#ifndef DIB_MINBLOCKS4
-#define DIB_MINBLOCKS4 10                         // ptxas settles on 96 registers (~60 B of spills) for both 9 and 10;
-                                              // 8 (124 registers, no spills, 16 warps/SM) measured slower
+#ifndef DIB_WARPS_F6
+#define DIB_WARPS_F6 14
 #endif
-#ifndef DIB_MINBLOCKS6
-#define DIB_MINBLOCKS6 8                          // 128 registers (6 -> 168 registers measured 2 % slower)
+#ifndef DIB_WARPS_D4
+#define DIB_WARPS_D4 14
 #endif
-constexpr int kThreads = DIB_THREADS;   // threads per problem (CTA)
-constexpr int kWarps = kThreads / 32;
-
+#ifndef DIB_WARPS_D6
+#define DIB_WARPS_D6 10
+#endif
+#ifndef DIB_CTAS_PER_SM
+#define DIB_CTAS_PER_SM 1                     // tuning: e.g. 10 warps x 2 CTAs (smaller help domain, same warps per SM)
+#endif
+template <typename CT, int P> struct Cfg;
+template <> struct Cfg<float, 4> { static constexpr int kWarps = DIB_WARPS_F4; };
+template <> struct Cfg<float, 6> { static constexpr int kWarps = DIB_WARPS_F6; };
+template <> struct Cfg<double, 4> { static constexpr int kWarps = DIB_WARPS_D4; };
+template <> struct Cfg<double, 6> { static constexpr int kWarps = DIB_WARPS_D6; };
 
 struct Cam {
   double fx, fy, cx, cy, W1, H1, hW, hH;
@@ -73,6 +87,7 @@ struct NAcc {
 __host__ __device__ constexpr int tri(int P, int j, int k) {   // j <= k
   return j * P - j * (j - 1) / 2 + (k - j);
 }
+
 
 // ------------------------------------------------------------------------------------------
 // Pose constants.
@@ -232,30 +247,6 @@ __device__ __forceinline__ bool point_rows(double px, double py, double pz, int 
   return true;
 }
 
-template <int P>
-__device__ __forceinline__ void point_accumulate(double px, double py, double pz, int lab, const Cam& cam,
-                                                 const PoseConst& pc, double* acc) {
-  double r[3], J[3][P];
-  int nrows;
-  if (!point_rows<P>(px, py, pz, lab, cam, pc, r, J, &nrows)) return;
-  if (lab == 0) {
-    const double s = r[0] * r[0];
-    const double sum = 1.0 + s;
-    const double w = 1.0 / sum;
-    acc[0] += 0.5 * log(sum);
-    rank1<P, double*>(acc, J[0], w, r[0]);
-  } else {
-    const double s = r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
-    const double sum = 1.0 + s;
-    const double w = 1.0 / sum;
-    acc[0] += 0.5 * log(sum);
-    // rows with a zero selector are exactly zero and contribute nothing
-    if (r[0] != 0.0 || J[0][P - 3] != 0.0) rank1<P, double*>(acc, J[0], w, r[0]);
-    if (r[1] != 0.0 || J[1][P - 2] != 0.0) rank1<P, double*>(acc, J[1], w, r[1]);
-    if (J[2][P - 1] != 0.0) rank1<P, double*>(acc, J[2], w, r[2]);
-  }
-}
-
 // ------------------------------------------------------------------------------------------
 // Branch-free evaluators used by the solver's hot loop.  Batches are homogeneous in the label and
 // every lane evaluates two points, so that two independent dependency chains are in flight per
@@ -272,9 +263,16 @@ __device__ __forceinline__ void project_point(double px, double py, double pz, b
                                               const PoseConst& pc, Proj<P>& o) {
   constexpr int NR = P - 3;
   if (!valid) { px = 0.0; py = 0.0; pz = 0.0; }
-  const double rx = fma(pc.R[0], px, fma(pc.R[1], py, pc.R[2] * pz));
-  const double ry_ = fma(pc.R[3], px, fma(pc.R[4], py, pc.R[5] * pz));
-  const double rz = fma(pc.R[6], px, fma(pc.R[7], py, pc.R[8] * pz));
+  double rx, ry_, rz;
+  if (P == 4) {        // R = Ry(ry): rows (c 0 s), (0 1 0), (-s 0 c); the zero / unit entries are exact, so this is
+    rx = fma(pc.R[0], px, pc.R[2] * pz);            // bit-identical to the general form below
+    ry_ = py;
+    rz = fma(pc.R[6], px, pc.R[8] * pz);
+  } else {
+    rx = fma(pc.R[0], px, fma(pc.R[1], py, pc.R[2] * pz));
+    ry_ = fma(pc.R[3], px, fma(pc.R[4], py, pc.R[5] * pz));
+    rz = fma(pc.R[6], px, fma(pc.R[7], py, pc.R[8] * pz));
+  }
   o.X = rx + pc.t[0]; o.Y = ry_ + pc.t[1]; o.Z = rz + pc.t[2];
   const double zs = (valid && o.Z != 0.0) ? o.Z : 1.0;     // keeps masked lanes finite
   o.iz = 1.0 / zs;
@@ -488,82 +486,40 @@ __device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab,
 // loaded point by point.  (frustum_prepare_batch sorts points by (label, Morton cell) so that
 // groups are spatially compact and label-pure; unsorted clouds still work, they just cull less.)
 //
-// Global layout per sample: rounds x [8 fields][kThreads] floats, group id of slot (round r, warp
-// w, lane l) = r * kThreads + l * kWarps + w  -- neighbouring groups are dealt round-robin to the
-// warps (load balance) while each warp reads consecutive words (no bank conflicts).
-// Fields: cx cy cz hx hy hz flags(bit0: has label 0, bit1: has label 1) pad.
+// Global layout per sample: rounds x [8 fields][32] floats; round r holds groups 32 r .. 32 r + 31, one
+// per lane, so a warp reads consecutive words.  Fields: cx cy cz hx hy hz flags(bit0: has label 0,
+// bit1: has label 1) pad.
 // ------------------------------------------------------------------------------------------
 constexpr int kBoxFields = 8;
-constexpr int kBoxRoundFloats = kBoxFields * kThreads;
-#ifndef DIB_BOX_ROUNDS
-#define DIB_BOX_ROUNDS 8
-#endif
-#ifndef DIB_ACC_SMEM
-#define DIB_ACC_SMEM 1                        // 1: the per-lane accumulators live in shared memory ([N][32] per warp) instead of
-#endif                                        //    registers: fewer spills at 96 registers (-1.8 % kernel time); going on to 12 or
-                                              //    16 CTAs/SM (80 / 64 registers) measured slower again
+constexpr int kRoundGroups = 32;                         // groups per round = one per lane
+constexpr int kRoundPoints = kRoundGroups * 32;          // 1024 points
+constexpr int kBoxRoundFloats = kBoxFields * kRoundGroups;
 #ifndef DIB_RING
 #define DIB_RING 128                          // pending-ring entries per warp and label (power of two)
 #endif
-#ifndef DIB_PACKED
-#define DIB_PACKED 1                          // 1: frustum_boxes_kernel also writes a packed {x, y, z, label} record per point into the
-#endif                                        //    workspace and the solver loads an undecided group's points with ONE 16-byte load per lane
-                                              //    instead of four (the x/y/z/label arrays of the canonical record are then read once per launch)
-#ifndef DIB_GROUP_PIPE
-#define DIB_GROUP_PIPE 0                      // 1: software-pipeline the undecided-group loads one step ahead (registers)
-#endif
-#ifndef DIB_GROUP_TMA
-#define DIB_GROUP_TMA 0                       // 1: undecided groups are staged by cp.async.bulk (TMA engine) into a per-warp
-#endif                                        //    double buffer one step ahead; 0: plain coalesced loads into registers.
-                                              //    Measured on B200, same call (profiles/r01_sweep_build_params.jsonl):
-                                              //    TMA 133 ms vs loads 103 ms per 512x60 problems -- 128-byte bulk copies
-                                              //    cost more than the 8 coalesced loads they replace.
 #ifndef DIB_GPS
 #define DIB_GPS 2                             // undecided groups fetched + classified per step
 #endif
-#ifndef DIB_EXACT_ILP
-#define DIB_EXACT_ILP 1                       // exact-path entries per lane per batch (1 or 2); 1 fits 96 registers
-                                              // -> 10 CTAs/SM, measured faster than ILP 2 at 8 CTAs/SM
+#ifndef DIB_SLICE_ROUNDS
+#define DIB_SLICE_ROUNDS 4                    // rounds (of 1024 points) per slice: 20480 points = 20 rounds = 5 slices
 #endif
-#ifndef DIB_BOX_SMEM
-#define DIB_BOX_SMEM 0                        // 1: table bulk-copied (TMA engine) into shared memory per problem; 0: read via L1/L2
-                                              // (measured faster on B200: profiles/r01_sweep_build_params.jsonl)
-#endif
-constexpr int kBoxRounds = DIB_BOX_SMEM ? DIB_BOX_ROUNDS : 1;   // rounds resident in shared memory (x kThreads x 32 points)
+constexpr int kMaxSlices = 12;                // slices per pass held in shared memory (larger clouds get longer slices)
 
-__host__ __device__ inline int box_rounds(int n) { return (((n + 31) >> 5) + kThreads - 1) / kThreads; }
+__host__ __device__ inline int box_rounds(int n) { return (n + kRoundPoints - 1) / kRoundPoints; }
+// rounds per slice for a cloud of `rounds` rounds: the configured length, stretched for very large clouds so that
+// the pass never has more than kMaxSlices slices.  Depends on the cloud size only (results must not depend on
+// the batch or on who computes a slice).
+__host__ __device__ inline int slice_len(int rounds, int want) {
+  int len = want < 1 ? 1 : want;
+  const int need = (rounds + kMaxSlices - 1) / kMaxSlices;
+  return len < need ? need : len;
+}
 
-// Self-contained record of a point: the element of the packed per-launch copy (DIB_PACKED) and of the
+// Self-contained record of a point: the element of the packed per-launch copy and of the
 // per-warp rings of maybe-active points.
 template <typename CT> struct Entry;
 template <> struct alignas(16) Entry<float> { float x, y, z; int lab; };
 template <> struct alignas(16) Entry<double> { double x, y, z; long long lab; };
-
-#ifndef DIB_PK_LDG
-#define DIB_PK_LDG 0                          // 1: packed records are read with ld.global.nc (LDG) instead of generic loads
-#endif
-template <typename CT> __device__ __forceinline__ Entry<CT> load_entry(const Entry<CT>* p);
-template <> __device__ __forceinline__ Entry<float> load_entry<float>(const Entry<float>* p) {
-#if DIB_PK_LDG
-  const int4 v = __ldg(reinterpret_cast<const int4*>(p));
-  Entry<float> e;
-  e.x = __int_as_float(v.x); e.y = __int_as_float(v.y); e.z = __int_as_float(v.z); e.lab = v.w;
-  return e;
-#else
-  return *p;
-#endif
-}
-template <> __device__ __forceinline__ Entry<double> load_entry<double>(const Entry<double>* p) {
-#if DIB_PK_LDG
-  const int4 a = __ldg(reinterpret_cast<const int4*>(p)), b = __ldg(reinterpret_cast<const int4*>(p) + 1);
-  Entry<double> e;
-  e.x = __hiloint2double(a.y, a.x); e.y = __hiloint2double(a.w, a.z); e.z = __hiloint2double(b.y, b.x);
-  e.lab = (long long)(((unsigned long long)(unsigned)b.w << 32) | (unsigned)b.z);
-  return e;
-#else
-  return *p;
-#endif
-}
 
 template <typename CT>
 __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict__ xyz,
@@ -574,7 +530,7 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
   const int s = blockIdx.y;
   const int lane = threadIdx.x & 31;
   const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gid >= rounds_max * kThreads) return;
+  if (gid >= rounds_max * kRoundGroups) return;
   const int n = n_pts ? n_pts[s] : n_stride;
   const int i = gid * 32 + lane;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
@@ -591,9 +547,9 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
       lo[0] = hi[0] = (double)e.x; lo[1] = hi[1] = (double)e.y; lo[2] = hi[2] = (double)e.z;
     }
   }
-  // packed copy: every slot of the sample's rounds x kThreads x 32 grid is written (padding and ignored labels
+  // packed copy: every slot of the sample's rounds x 32 x 32 grid is written (padding and ignored labels
   // as label -1), so the solver needs no bounds test
-  if (packed) packed[(size_t)s * rounds_max * (kThreads * 32) + i] = e;
+  packed[(size_t)s * rounds_max * kRoundPoints + i] = e;
 #pragma unroll
   for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -603,9 +559,8 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
     }
   const unsigned m0 = __ballot_sync(0xffffffffu, lab == 0), m1 = __ballot_sync(0xffffffffu, lab == 1);
   if (lane == 0) {
-    const int r = gid / kThreads, q = gid % kThreads;
-    const int w = q % kWarps, l = q / kWarps;
-    float* rec = table + ((size_t)s * rounds_max + r) * kBoxRoundFloats + (w * 32 + l);
+    const int r = gid / kRoundGroups, q = gid % kRoundGroups;
+    float* rec = table + ((size_t)s * rounds_max + r) * kBoxRoundFloats + q;
     const int flags = (m0 ? 1 : 0) | (m1 ? 2 : 0);
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
@@ -617,18 +572,17 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
         const double hd = fmax(hi[c] - (double)cf, (double)cf - lo[c]);
         hf = (float)(hd * 1.000001 + (fabs(cd) + hd) * 1.3e-7 + 1e-30);
       }
-      rec[c * kThreads] = cf;
-      rec[(3 + c) * kThreads] = hf;
+      rec[c * kRoundGroups] = cf;
+      rec[(3 + c) * kRoundGroups] = hf;
     }
-    rec[6 * kThreads] = __int_as_float(flags);
-    rec[7 * kThreads] = 0.f;
+    rec[6 * kRoundGroups] = __int_as_float(flags);
+    rec[7 * kRoundGroups] = 0.f;
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Shared-memory layout of one CTA.
+// Shared-memory layout.
 // ------------------------------------------------------------------------------------------
-
 struct LsSample {
   double x, value, gradient;
   int value_valid, gradient_valid;
@@ -646,58 +600,60 @@ struct LMState {
   LsSample lower, prev, cur;
   double xt[P];          // point of the pending evaluation
   int reuse_diag, step_ok, invalid, iteration, max_iter;
-  int phase;             // 0 initial, 1 line-search sample, 2 candidate after failed line search
+  int phase;             // 0 initial, 1 line-search sample, 2 candidate after failed line search, 3 cost at an infeasible start
   int ls_iter, evals, ls_steps, term;
-  double scratch[72];    // line-search interpolation workspace (shared memory, see interpolating_min_step)
 };
 
-constexpr int kBatch = 32 * DIB_EXACT_ILP;   // entries evaluated per exact-path batch
-constexpr int kRing = DIB_RING;          // pending ring per label: < kBatch carried + at most DIB_GPS x 32 appended per step
+constexpr int kBatch = 32;                // entries evaluated per exact-path batch (one per lane)
+constexpr int kRing = DIB_RING;           // pending ring per label: < kBatch carried + at most DIB_GPS x 32 appended per step
 static_assert(kBatch + 32 * DIB_GPS <= kRing, "ring too small");
 
-// Per-warp staging buffer of one step's undecided groups (filled by bulk copies).
-template <typename CT>
-struct alignas(16) GroupStage {
-  CT x[DIB_GPS][32];
-  CT y[DIB_GPS][32];
-  CT z[DIB_GPS][32];
-  int8_t lab[DIB_GPS][32];
+// Scratch of the warp that EXECUTES a slice (its own or a CTA-mate's).
+template <typename CT, int P>
+struct WarpScratch {
+  Entry<CT> ring[2][kRing];               // [label 0 | label 1] pending rings
+  double accs[NAcc<P>::N][32];            // per-lane accumulators (column = lane: conflict-free)
 };
 
+// State of the problem a warp OWNS.  Helpers read pose/cls/cam/pk/box and write part[k]; everything else is
+// touched by the owner only.
 template <typename CT, int P>
-struct Smem {
-  // Staging buffers of the optional TMA variants shrink to stubs when those variants are compiled out: with
-  // them the CTA needed 23.2 KB and shared memory capped the SM at 9 CTAs although registers allow 10.
-  alignas(16) float box[kBoxRounds][DIB_BOX_SMEM ? kBoxRoundFloats : 4];   // bulk-copied (TMA engine) once per problem
-  Entry<CT> list[kWarps][2][kRing];                     // [label 0 | label 1] pending rings
-#if DIB_ACC_SMEM
-  double accs[kWarps][NAcc<P>::N][32];                  // per-lane accumulators (column = lane: conflict-free)
-#endif
-#if DIB_GROUP_TMA
-  GroupStage<CT> gstage[kWarps][2];                     // double-buffered group staging, private to each warp
-#endif
-  alignas(8) uint64_t gbar[kWarps][2];                  // their mbarriers
-  alignas(8) uint64_t full;                             // mbarrier of the box-table copy
-  double red[kWarps][NAcc<P>::N];
+struct ProbCtx {
+  double part[kMaxSlices][NAcc<P>::N];    // slice sums of the open pass (line-search scratch between passes)
   double tot[NAcc<P>::N];
   PoseConst pose;
   ClassConst cls;
   Cam cam;
   LMState<P> lm;
-  int problem;       // current problem id (broadcast)
-  int go;            // 1 = another evaluation requested
+  const Entry<CT>* pk;                    // packed copy of the sample's cloud
+  const float* box;                       // its box table
+  int rounds, slice_rounds, nslices;
+  int prob;
+  int next_slice;                         // claim counter of the open pass (>= nslices: nothing left to claim)
+  int done;                               // slices of the open pass that are finished
 };
+static_assert(kMaxSlices * NAcc<4>::N >= 72, "part[] doubles as the 72-double line-search scratch");
 
-// Box test of one group by one lane: true if the group needs per-point work.
+template <typename CT, int P>
+struct Smem {
+  WarpScratch<CT, P> scratch[Cfg<CT, P>::kWarps];
+  ProbCtx<CT, P> ctx[Cfg<CT, P>::kWarps];
+  unsigned open_mask;                     // bit w: warp w's open pass may still have unclaimed slices
+  int n_active;                           // warps that own a problem or may still fetch one
+};
+static_assert(sizeof(Smem<float, 4>) * DIB_CTAS_PER_SM <= 227 * 1024, "4-DoF shared memory");
+static_assert(sizeof(Smem<float, 6>) * DIB_CTAS_PER_SM <= 227 * 1024, "6-DoF shared memory");
+static_assert(sizeof(Smem<double, 4>) * DIB_CTAS_PER_SM <= 227 * 1024, "4-DoF f64 shared memory");
+static_assert(sizeof(Smem<double, 6>) * DIB_CTAS_PER_SM <= 227 * 1024, "6-DoF f64 shared memory");
+
 // One box record as seven registers (cx cy cz hx hy hz flags).
 struct BoxRec {
   float v[7];
 };
 
-template <int SMEM>
 __device__ __forceinline__ void box_load(const float* f, int slot, BoxRec& b) {
 #pragma unroll
-  for (int k = 0; k < 7; ++k) b.v[k] = SMEM ? f[k * kThreads + slot] : __ldg(f + k * kThreads + slot);
+  for (int k = 0; k < 7; ++k) b.v[k] = __ldg(f + k * kRoundGroups + slot);
 }
 
 // Box test of one group by one lane: true if the group needs per-point work.
@@ -723,254 +679,68 @@ __device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst&
 }
 
 // ------------------------------------------------------------------------------------------
-// One pass over a cloud (all threads must call): box tests -> coalesced loads of the undecided
-// groups -> per-point fp32 culling -> ordered compaction into the warp's pending rings -> exact
-// fp64 evaluation of 64 pending points at a time (two per lane, label-homogeneous) -> fixed-order
-// block reduction into sm.tot.  Warps never synchronise with each other inside the pass.
-// `boxes_resident` says the sample's whole table already sits in sm.box.
+// One slice of a pass, executed by one warp (all 32 lanes call): rounds [r_begin, r_end) of the cloud.
+// Box tests -> coalesced 16-byte loads of the undecided groups -> per-point fp32 culling -> ordered
+// compaction into the executing warp's pending rings -> exact fp64 evaluation of 32 pending points at a time
+// (one per lane, label-homogeneous) -> fixed-order reduction of the 32 lanes into part[0..N).
+// The result depends only on (cloud, pose, r_begin, r_end): rings and accumulators start empty and are
+// drained at the end of the slice, so any warp computes the same bits.
 // ------------------------------------------------------------------------------------------
 template <typename CT, int P>
-__device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* lab_s, const Entry<CT>* pk_s,
-                               int n_stride, int n, const float* box_s, bool boxes_resident, uint32_t& box_phase, uint32_t& gphase) {
+__device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx<CT, P>& pb, int r_begin, int r_end,
+                                           double* part, int lane) {
   constexpr int N = NAcc<P>::N;
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
   const unsigned lt_mask = (1u << lane) - 1u;
-  const int rounds = box_rounds(n);
-#if DIB_ACC_SMEM
-  SmemAcc acc{&sm.accs[warp][0][lane]};
-#else
-  double acc[N];
-#endif
+  SmemAcc acc{&ws.accs[0][lane]};
 #pragma unroll
   for (int j = 0; j < N; ++j) acc[j] = 0.0;
-#if DIB_ACC_SMEM
-  const SmemAcc acc_view = acc;
-#else
-  double* const acc_view = acc;
-#endif
-  const Cam& cam = sm.cam;
-  const PoseConst& pc = sm.pose;
-  const ClassConst& cc = sm.cls;
-  Entry<CT>* ring0 = sm.list[warp][0];
-  Entry<CT>* ring1 = sm.list[warp][1];
+  const Cam& cam = pb.cam;
+  const PoseConst& pc = pb.pose;
+  const ClassConst& cc = pb.cls;
+  const Entry<CT>* pk_s = pb.pk;
+  const float* box_s = pb.box;
+  Entry<CT>* ring0 = ws.ring[0];
+  Entry<CT>* ring1 = ws.ring[1];
   int head0 = 0, pend0 = 0, head1 = 0, pend1 = 0;   // warp-uniform
   double prod = 1.0;                                  // per-lane product of (1 + s), renormalised
   int expo = 0;
   BoxRec box_cur, box_nxt;
 #pragma unroll
   for (int k = 0; k < 7; ++k) { box_cur.v[k] = 0.f; box_nxt.v[k] = 0.f; }
-#if !DIB_BOX_SMEM
-  if (rounds > 0) box_load<0>(box_s, warp * 32 + lane, box_nxt);
-#endif
+  if (r_begin < r_end) box_load(box_s + (size_t)r_begin * kBoxRoundFloats, lane, box_nxt);
 
-  // Rounds r = 0 .. rounds-1 test one box per lane; the extra last round only drains what is left,
+  // Rounds r_begin .. r_end-1 test one box per lane; the extra last round only drains what is left,
   // so each exact evaluator has ONE code instance.
 #pragma unroll 1
-  for (int r = 0; r <= rounds; ++r) {
+  for (int r = r_begin; r <= r_end; ++r) {
     unsigned mask = 0;
     int threshold = 1;
-    if (r < rounds) {
+    if (r < r_end) {
       threshold = kBatch;
-      if (DIB_BOX_SMEM && !boxes_resident && (r % kBoxRounds) == 0) {
-        // clouds larger than the resident window: stream the table chunk by chunk, every pass
-        __syncthreads();
-        if (tid == 0) {
-          int nr = rounds - r;
-          if (nr > kBoxRounds) nr = kBoxRounds;
-          const uint32_t bytes = (uint32_t)nr * kBoxRoundFloats * sizeof(float);
-          mbar_expect_tx(&sm.full, bytes);
-          bulk_g2s(&sm.box[0][0], box_s + (size_t)r * kBoxRoundFloats, bytes, &sm.full);
-        }
-        mbar_wait(&sm.full, box_phase & 1);
-        ++box_phase;
-      }
-#if DIB_BOX_SMEM
-      box_load<1>(sm.box[r % kBoxRounds], warp * 32 + lane, box_cur);
-#else
       box_cur = box_nxt;                              // loaded while the previous round was processed
-      if (r + 1 < rounds) box_load<0>(box_s + (size_t)(r + 1) * kBoxRoundFloats, warp * 32 + lane, box_nxt);
-#endif
+      if (r + 1 < r_end) box_load(box_s + (size_t)(r + 1) * kBoxRoundFloats, lane, box_nxt);
       mask = __ballot_sync(0xffffffffu, box_undecided(box_cur, cc));
     }
-#if DIB_GROUP_TMA
-    // Undecided groups are taken DIB_GPS at a time and STAGED BY THE TMA ENGINE: lane 0 issues one
-    // cp.async.bulk per coordinate array and group (128 B of x, y, z and 32 B of labels) into this warp's
-    // double buffer, one step ahead of its use, completion signalled on the slot's mbarrier.  While the
-    // copies fly the warp drains pending exact-path batches; then it classifies the staged groups
-    // (independent instruction streams) and appends.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
-    int cur_cnt = 0, cur_g[DIB_GPS], slot = 0;
-    auto take_and_issue = [&](int which, int* g_out) -> int {
-      int cnt = 0;
-#pragma unroll
-      for (int u = 0; u < DIB_GPS; ++u) {
-        g_out[u] = -1;
-        if (mask) {
-          const int b = __ffs(mask) - 1;
-          mask &= mask - 1;
-          g_out[u] = r * kThreads + b * kWarps + warp;
-          ++cnt;
-        }
-      }
-      if (cnt && lane == 0) {
-        GroupStage<CT>& gs = sm.gstage[warp][which];
-        uint64_t* bar = &sm.gbar[warp][which];
-        uint32_t bytes = 0;
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u)
-          if (g_out[u] >= 0) {
-            int c = n_stride - g_out[u] * 32;           // points of this group inside the row (multiple of 16)
-            c = c > 32 ? 32 : c;
-            bytes += (uint32_t)c * (3u * sizeof(CT) + 1u);
-          }
-        mbar_expect_tx(bar, bytes);
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u)
-          if (g_out[u] >= 0) {
-            const int base = g_out[u] * 32;
-            int c = n_stride - base;
-            c = c > 32 ? 32 : c;
-            bulk_g2s(gs.x[u], xyz_s + base, (uint32_t)c * sizeof(CT), bar);
-            bulk_g2s(gs.y[u], xyz_s + n_stride + base, (uint32_t)c * sizeof(CT), bar);
-            bulk_g2s(gs.z[u], xyz_s + 2 * (size_t)n_stride + base, (uint32_t)c * sizeof(CT), bar);
-            bulk_g2s(gs.lab[u], lab_s + base, (uint32_t)c, bar);
-          }
-      }
-      return cnt;
-    };
-    if (mask) cur_cnt = take_and_issue(slot, cur_g);
-#pragma unroll 1
-    do {
-      int nxt_cnt = 0, nxt_g[DIB_GPS];
-#pragma unroll
-      for (int u = 0; u < DIB_GPS; ++u) nxt_g[u] = -1;
-      if (mask) nxt_cnt = take_and_issue(slot ^ 1, nxt_g);
-#pragma unroll 1
-      while (pend0 >= threshold) {
-        __syncwarp();
-        const int take = pend0 < kBatch ? pend0 : kBatch;
-        const Entry<CT> ea = ring0[(head0 + lane) & (kRing - 1)];
-        Out0<P> oa;
-        eval_outside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
-#if DIB_EXACT_ILP == 2
-        const Entry<CT> eb = ring0[(head0 + 32 + lane) & (kRing - 1)];
-        Out0<P> ob;
-        eval_outside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
-        prod *= oa.s1 * ob.s1;
-#else
-        prod *= oa.s1;
-#endif
-        renorm_product(prod, expo);
-        rank1<P, decltype(acc_view)>(acc_view, oa.J, oa.w, oa.r);
-#if DIB_EXACT_ILP == 2
-        rank1<P, decltype(acc_view)>(acc_view, ob.J, ob.w, ob.r);
-#endif
-        head0 = (head0 + take) & (kRing - 1);
-        pend0 -= take;
-      }
-#pragma unroll 1
-      while (pend1 >= threshold) {
-        __syncwarp();
-        const int take = pend1 < kBatch ? pend1 : kBatch;
-        const Entry<CT> ea = ring1[(head1 + lane) & (kRing - 1)];
-        Out1<P> oa;
-        eval_inside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
-#if DIB_EXACT_ILP == 2
-        const Entry<CT> eb = ring1[(head1 + 32 + lane) & (kRing - 1)];
-        Out1<P> ob;
-        eval_inside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
-        prod *= oa.s1 * ob.s1;
-#else
-        prod *= oa.s1;
-#endif
-        renorm_product(prod, expo);
-        accumulate_inside<P, decltype(acc_view)>(acc_view, oa);
-#if DIB_EXACT_ILP == 2
-        accumulate_inside<P, decltype(acc_view)>(acc_view, ob);
-#endif
-        head1 = (head1 + take) & (kRing - 1);
-        pend1 -= take;
-      }
-      if (cur_cnt) {
-        mbar_wait(&sm.gbar[warp][slot], (gphase >> slot) & 1u);
-        gphase ^= 1u << slot;
-        const GroupStage<CT>& gs = sm.gstage[warp][slot];
-        CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-        int glab[DIB_GPS];
-        bool mb[DIB_GPS];
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) {
-          const bool in = cur_g[u] >= 0 && cur_g[u] * 32 + lane < n;
-          gx[u] = in ? gs.x[u][lane] : (CT)0; gy[u] = in ? gs.y[u][lane] : (CT)0; gz[u] = in ? gs.z[u][lane] : (CT)0;
-          glab[u] = in ? (int)gs.lab[u][lane] : -1;
-        }
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) {
-          const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
-          const unsigned m0 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 0);
-          if (mb[u]) {
-            Entry<CT> e;
-            e.x = gx[u]; e.y = gy[u]; e.z = gz[u]; e.lab = glab[u];
-            if (glab[u]) ring1[(head1 + pend1 + __popc(m1 & lt_mask)) & (kRing - 1)] = e;
-            else         ring0[(head0 + pend0 + __popc(m0 & lt_mask)) & (kRing - 1)] = e;
-          }
-          pend0 += __popc(m0);
-          pend1 += __popc(m1);
-        }
-      }
-      cur_cnt = nxt_cnt;
-#pragma unroll
-      for (int u = 0; u < DIB_GPS; ++u) cur_g[u] = nxt_g[u];
-      slot ^= 1;
-    } while (cur_cnt);
-#else
     // Undecided groups are taken DIB_GPS at a time.  Their loads are issued first, then the pending
     // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
     // (independent instruction streams) and appended.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
-    auto load_groups = [&](CT* lx, CT* ly, CT* lz, int* ll) -> bool {
-      const bool any = mask != 0;
-      if (any) {
+#pragma unroll 1
+    do {
+      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+      int glab[DIB_GPS];
+      const bool have = mask != 0;
+      if (have) {
 #pragma unroll
         for (int u = 0; u < DIB_GPS; ++u) {
-          ll[u] = -1; lx[u] = 0; ly[u] = 0; lz[u] = 0;
+          glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
           if (mask) {
             const int b = __ffs(mask) - 1;
             mask &= mask - 1;
-            const int i = (r * kThreads + b * kWarps + warp) * 32 + lane;      // this lane's point
-#if DIB_PACKED
-            const Entry<CT> e = load_entry<CT>(pk_s + i);
-            ll[u] = (int)e.lab; lx[u] = e.x; ly[u] = e.y; lz[u] = e.z;
-#else
-            if (i < n) {
-              ll[u] = lab_s[i];
-              lx[u] = xyz_s[i]; ly[u] = xyz_s[n_stride + i]; lz[u] = xyz_s[2 * (size_t)n_stride + i];
-            }
-#endif
+            const Entry<CT> e = pk_s[(size_t)(r * kRoundGroups + b) * 32 + lane];      // this lane's point
+            glab[u] = (int)e.lab; gx[u] = e.x; gy[u] = e.y; gz[u] = e.z;
           }
         }
       }
-      return any;
-    };
-#if DIB_GROUP_PIPE
-    // register software pipeline: the NEXT DIB_GPS groups are loaded before the current ones are classified,
-    // so the L2 latency of a group is covered by the classification of the previous one as well
-    CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-    int glab[DIB_GPS];
-    bool have = load_groups(gx, gy, gz, glab);
-#endif
-#pragma unroll 1
-    do {
-#if DIB_GROUP_PIPE
-      CT nx[DIB_GPS], ny[DIB_GPS], nz[DIB_GPS];
-      int nlab[DIB_GPS];
-      const bool nhave = load_groups(nx, ny, nz, nlab);
-#else
-      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-      int glab[DIB_GPS];
-      const bool have = load_groups(gx, gy, gz, glab);
-#endif
 #pragma unroll 1
       while (pend0 >= threshold) {
         __syncwarp();
@@ -978,19 +748,9 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         const Entry<CT> ea = ring0[(head0 + lane) & (kRing - 1)];
         Out0<P> oa;
         eval_outside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
-#if DIB_EXACT_ILP == 2
-        const Entry<CT> eb = ring0[(head0 + 32 + lane) & (kRing - 1)];
-        Out0<P> ob;
-        eval_outside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
-        prod *= oa.s1 * ob.s1;
-#else
         prod *= oa.s1;
-#endif
         renorm_product(prod, expo);
-        rank1<P, decltype(acc_view)>(acc_view, oa.J, oa.w, oa.r);
-#if DIB_EXACT_ILP == 2
-        rank1<P, decltype(acc_view)>(acc_view, ob.J, ob.w, ob.r);
-#endif
+        rank1<P, SmemAcc>(acc, oa.J, oa.w, oa.r);
         head0 = (head0 + take) & (kRing - 1);
         pend0 -= take;
       }
@@ -1001,19 +761,9 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
         const Entry<CT> ea = ring1[(head1 + lane) & (kRing - 1)];
         Out1<P> oa;
         eval_inside<P>((double)ea.x, (double)ea.y, (double)ea.z, lane < take, cam, pc, oa);
-#if DIB_EXACT_ILP == 2
-        const Entry<CT> eb = ring1[(head1 + 32 + lane) & (kRing - 1)];
-        Out1<P> ob;
-        eval_inside<P>((double)eb.x, (double)eb.y, (double)eb.z, lane + 32 < take, cam, pc, ob);
-        prod *= oa.s1 * ob.s1;
-#else
         prod *= oa.s1;
-#endif
         renorm_product(prod, expo);
-        accumulate_inside<P, decltype(acc_view)>(acc_view, oa);
-#if DIB_EXACT_ILP == 2
-        accumulate_inside<P, decltype(acc_view)>(acc_view, ob);
-#endif
+        accumulate_inside<P, SmemAcc>(acc, oa);
         head1 = (head1 + take) & (kRing - 1);
         pend1 -= take;
       }
@@ -1038,73 +788,20 @@ __device__ void evaluate_cloud(Smem<CT, P>& sm, const CT* xyz_s, const int8_t* l
           pend1 += __popc(m1);
         }
       }
-#if DIB_GROUP_PIPE
-      if (nhave) {
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) { gx[u] = nx[u]; gy[u] = ny[u]; gz[u] = nz[u]; glab[u] = nlab[u]; }
-      }
-      have = nhave;
-    } while (have);
-#else
     } while (mask);
-#endif
-#endif
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
-  // Fixed-order reduction.  The pending rings are empty now, so each warp reuses its ring memory as a
-  // [N][33] scratch: lane j sums accumulator j over lanes 0..31 in order, then thread j sums the
-  // warps in order.  (A loop over shared memory instead of ~300 unrolled shuffles: this epilogue
-  // runs once per pass and its code size matters more than its speed.)
-#if DIB_ACC_SMEM
-  __syncwarp();
-  if (lane < N) {                                   // the accumulators already sit in shared memory as [N][32]
-    double v = 0.0;
-#pragma unroll 4
-    for (int l = 0; l < 32; ++l) v += sm.accs[warp][lane][l];
-    sm.red[warp][lane] = v;
-  }
-#else
-  double* scratch = reinterpret_cast<double*>(sm.list[warp]);
-  static_assert(sizeof(Entry<CT>) * 2 * kRing >= sizeof(double) * N * 33, "ring too small for the reduction scratch");
-  __syncwarp();
-#pragma unroll
-  for (int j = 0; j < N; ++j) scratch[j * 33 + lane] = acc[j];
+  // Fixed-order reduction: lane j sums accumulator j over the 32 lanes, starting at column j (a fixed order per
+  // accumulator; the rotation keeps the 32 reading lanes on 32 different banks).
   __syncwarp();
   if (lane < N) {
     double v = 0.0;
 #pragma unroll 4
-    for (int l = 0; l < 32; ++l) v += scratch[lane * 33 + l];
-    sm.red[warp][lane] = v;
+    for (int l = 0; l < 32; ++l) v += ws.accs[lane][(l + lane) & 31];   // rotated start: conflict-free, still a fixed order
+    part[lane] = v;
   }
-#endif
-  __syncthreads();
-  if (tid < N) {
-    double v = sm.red[0][tid];
-#pragma unroll
-    for (int w = 1; w < kWarps; ++w) v += sm.red[w][tid];
-    sm.tot[tid] = v;
-  }
-  __syncthreads();
-}
-
-// Loads a sample's whole box table into shared memory if it fits the resident window (all
-// threads call; returns true if resident).
-template <typename CT, int P>
-__device__ bool load_boxes(Smem<CT, P>& sm, const float* box_s, int n, uint32_t& box_phase) {
-  const int rounds = box_rounds(n);
-  if (!DIB_BOX_SMEM) return true;
-  if (rounds > kBoxRounds) return false;
-  if (rounds > 0) {
-    if (threadIdx.x == 0) {
-      const uint32_t bytes = (uint32_t)rounds * kBoxRoundFloats * sizeof(float);
-      mbar_expect_tx(&sm.full, bytes);
-      bulk_g2s(&sm.box[0][0], box_s, bytes, &sm.full);
-    }
-    mbar_wait(&sm.full, box_phase & 1);
-    ++box_phase;
-  }
-  return true;
+  __syncwarp();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1418,7 +1115,8 @@ __device__ __noinline__ int lm_next_step(LMState<P>& st) {
     }
     if (!ok || !(mcc > 0.0)) {
       if (++st.invalid >= 5) { st.term = 5; return LM_DONE; }
-      st.radius *= 0.5;
+      st.radius = st.radius / st.dec;      // LevenbergMarquardtStrategy::StepIsInvalid() == StepRejected(0)
+      st.dec *= 2.0;
       st.reuse_diag = 1;
       continue;
     }
@@ -1477,8 +1175,12 @@ __device__ __noinline__ int lm_after_candidate(LMState<P>& st, const double* tot
 
 // Consumes the evaluation at st.xt (totals in tot).  Returns LM_EVAL with a new st.xt or LM_DONE.
 template <int P>
-__device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
+__device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot, double* scratch) {
   constexpr int NA = NAcc<P>::NA;
+  if (st.phase == 3) {                     // infeasible start: Problem::Evaluate at the untouched init, no solve
+    st.cost = tot[0];
+    return LM_DONE;
+  }
   ++st.evals;
   if (st.phase == 0) {
     st.cost = tot[0];
@@ -1512,7 +1214,7 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
     bool fail = st.ls_iter >= 20;
     double a = 0.0;
     if (!fail) {
-      a = interpolating_min_step(st.lower, st.prev, cur, 1e-3 * cur.x, 0.6 * cur.x, st.scratch);
+      a = interpolating_min_step(st.lower, st.prev, cur, 1e-3 * cur.x, 0.6 * cur.x, scratch);
       if (a * st.dmax < 1e-9) fail = true;
     }
     if (fail) {
@@ -1534,7 +1236,7 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
   return lm_after_candidate<P>(st, tot);
 }
 
-// Returns LM_EVAL (st.xt set) or LM_DONE (infeasible start).
+// Sets st.xt and returns LM_EVAL (an infeasible start asks for ONE cost-only pass at the init, phase 3).
 template <int P>
 __device__ __noinline__ int lm_begin(LMState<P>& st, const double* init4, const double* lb3, const double* ub3, int max_iter) {
   constexpr int toff = P - 3;
@@ -1546,17 +1248,17 @@ __device__ __noinline__ int lm_begin(LMState<P>& st, const double* init4, const 
   st.max_iter = max_iter;
   st.iteration = 0; st.evals = 0; st.ls_steps = 0; st.term = -1; st.invalid = 0;
   st.radius = 1e4; st.dec = 2.0; st.reuse_diag = 0; st.step_ok = 1; st.phase = 0;
-  st.cost = 0.0; st.grad_max = 0.0;
+  st.cost = 0.0; st.grad_max = 0.0; st.mcc = 0.0; st.cur.x = 1.0;
   #pragma unroll 1
   for (int j = 0; j < P; ++j) st.g[j] = 0.0;
   #pragma unroll 1
   for (int j = 0; j < P; ++j)
-    if (st.x[j] < st.lb[j] || st.x[j] > st.ub[j]) { st.term = 6; return LM_DONE; }
+    if (st.x[j] < st.lb[j] || st.x[j] > st.ub[j]) { st.term = 6; st.phase = 3; }
   double xn = 0.0;
   #pragma unroll 1
   for (int j = 0; j < P; ++j) { st.xt[j] = st.x[j]; xn += st.x[j] * st.x[j]; }
   st.x_norm = sqrt(xn);
-  return LM_EVAL;
+  return LM_EVAL;                          // always: an infeasible start still gets its cost evaluated (phase 3)
 }
 
 __device__ void make_cam(const double* K9, double H, double W, Cam* cam) {
@@ -1578,19 +1280,23 @@ struct SolveArgs {
   double* params_all;   // [S*I*6]
   double* cost_all;     // [S*I]
   int32_t* stats_all;   // [S*I*4]
-  unsigned int* queue;  // problem counter
-  const float* boxes;   // [S][rounds_max][8][kThreads] box table
-  const void* packed;   // [S][rounds_max * kThreads * 32] Entry<CT> (DIB_PACKED) or NULL
+  unsigned int* queue;  // problem counter (problems beyond the statically assigned first wave)
+  const float* boxes;   // [S][rounds_max][8][32] box table
+  const void* packed;   // [S][rounds_max * 1024] Entry<CT>
   int rounds_max;
   const int32_t* perm;  // [S][I] inits of each sample, longest-predicted first
   int chunk;            // samples per scheduling chunk
+  int slice_rounds;     // rounds per slice (before the kMaxSlices stretch)
+  double* trace;        // optional [S*I][trace_cap][kTraceRec] per-evaluation records, or NULL
+  int trace_cap;
 };
+
+constexpr int kTraceRec = 16;   // doubles per trace record, see include/deepi2p_b200.h (frustum_solve_traced_*)
 
 // Scheduling order.  Solve length correlates with how far an init's heading is from the centre of its
 // sample's inits (rank correlation ~0.6 with the number of evaluations), so each sample's inits are
 // ranked by that distance, longest-predicted first, and the queue walks chunks of samples rank-major:
-// the expensive solves start early and the end-of-kernel tail (idle SMs waiting for the last
-// long solves) shrinks, while concurrently running problems still share an L2-sized set of clouds.
+// the expensive solves start early, while concurrently running problems still share an L2-sized set of clouds.
 // perm [S][I]: perm[s][r] = init index of rank r.  Results do not depend on the order.
 __global__ void frustum_order_kernel(const double* __restrict__ init, int I, int32_t* __restrict__ perm) {
   extern __shared__ double key[];
@@ -1612,69 +1318,216 @@ __global__ void frustum_order_kernel(const double* __restrict__ init, int I, int
   }
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ int ld_volatile(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
+__device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+__device__ __forceinline__ void st_volatile(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
+
+// Lane 0 of the owner: publish the pass whose pose / classification constants were just written.
 template <typename CT, int P>
-__global__ void __launch_bounds__(kThreads, (P == 4) ? DIB_MINBLOCKS4 : DIB_MINBLOCKS6) frustum_solve_kernel(SolveArgs a) {
+__device__ __forceinline__ void open_pass(Smem<CT, P>& sm, ProbCtx<CT, P>& me, int warp) {
+  st_volatile(&me.done, 0);
+  __threadfence_block();                       // pose, cls, done before the pass becomes claimable
+  atomicOr(&sm.open_mask, 1u << warp);         // bit first: whoever claims the last slice clears it again
+  st_volatile(&me.next_slice, 0);
+}
+
+template <typename CT, int P>
+__device__ __forceinline__ void trace_record(const SolveArgs& a, const ProbCtx<CT, P>& me, int rec_idx, bool after) {
+  if (a.trace == nullptr || rec_idx >= a.trace_cap) return;
+  double* t = a.trace + ((size_t)me.prob * a.trace_cap + rec_idx) * kTraceRec;
+  const LMState<P>& st = me.lm;
+  if (!after) {
+    for (int j = 0; j < 6; ++j) t[j] = j < P ? st.xt[j] : 0.0;
+    t[6] = me.tot[0];
+    t[7] = st.cost;
+    t[8] = st.radius;
+    t[9] = (double)st.iteration;
+    t[10] = (double)st.phase;
+    t[13] = st.phase == 1 ? st.cur.x : 1.0;
+    t[14] = st.mcc;
+    t[15] = 1.0;                               // record valid
+  } else {
+    bool moved = true;                         // the evaluated point became the iterate <=> x == x_t now
+    for (int j = 0; j < P; ++j) moved = moved && (st.x[j] == t[j]);
+    t[11] = moved ? 1.0 : 0.0;
+    t[12] = (double)st.term;                   // -1 while running
+  }
+}
+
+enum { ST_FETCH = 0, ST_RUN = 1, ST_IDLE = 2 };
+
+template <typename CT, int P>
+__global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frustum_solve_kernel(SolveArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
-  const int tid = threadIdx.x;
-  if (tid == 0) {
-    mbar_init(&sm.full, 1);
-    for (int w = 0; w < kWarps; ++w) { mbar_init(&sm.gbar[w][0], 1); mbar_init(&sm.gbar[w][1], 1); }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  uint32_t box_phase = 0, gphase = 0;      // gphase: bit s = parity of this warp's staging slot s
+  constexpr int kW = Cfg<CT, P>::kWarps;
+  constexpr int N = NAcc<P>::N;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ProbCtx<CT, P>& me = sm.ctx[warp];
+  WarpScratch<CT, P>& ws = sm.scratch[warp];
+  if (lane == 0) { me.next_slice = 0; me.nslices = 0; me.done = 0; me.prob = -1; }
+  if (threadIdx.x == 0) { sm.open_mask = 0u; sm.n_active = kW; }
+  // Launch timeline for the benchmark (three 64-bit words after the queue counter, zeroed / primed by the host):
+  // kernel start, the moment the queue ran dry, the last CTA's exit -- all in globaltimer nanoseconds.
+  unsigned long long* tl = reinterpret_cast<unsigned long long*>(a.queue) + 1;
+  if (threadIdx.x == 0) atomicMin(tl + 0, global_ns());
+  __syncthreads();                               // the only CTA-wide barrier of the kernel
   const int total = a.S * a.I;
+  int state = ST_FETCH;                          // warp-uniform
+  bool first = true;
+  int n_rec = 0;                                 // trace records written for the current problem (lane 0)
 
   for (;;) {
-    if (tid == 0) {
-      const int q = (int)atomicAdd(a.queue, 1u);
-      int prob = q;
-      if (q < total) {
-        const int per_chunk = a.chunk * a.I;
-        const int c = q / per_chunk, within = q - c * per_chunk;
-        const int s0 = c * a.chunk;
-        const int gc = min(a.chunk, a.S - s0);             // samples in this chunk
-        const int r = within / gc, sc = s0 + (within - r * gc);
-        prob = sc * a.I + a.perm[(size_t)sc * a.I + r];
+    if (state == ST_FETCH) {
+      // First wave: problem ranks are dealt statically, rank-major over the CTAs, so that a batch smaller than
+      // the grid's warp count leaves every CTA with idle warps that help; later problems come from the queue.
+      int q = 0;
+      if (first) { q = warp * (int)gridDim.x + (int)blockIdx.x; first = false; }
+      else {
+        if (lane == 0) q = (int)gridDim.x * kW + (int)atomicAdd(a.queue, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
       }
-      sm.problem = prob;
-    }
-    __syncthreads();
-    const int prob = sm.problem;
-    if (prob >= total) break;
-    const int s = prob / a.I;
-    const CT* xyz_s = reinterpret_cast<const CT*>(a.xyz) + (size_t)s * 3 * a.n_stride;
-    const int8_t* lab_s = a.label + (size_t)s * a.n_stride;
-    const Entry<CT>* pk_s = reinterpret_cast<const Entry<CT>*>(a.packed) + (size_t)s * a.rounds_max * (kThreads * 32);
-    const float* box_s = a.boxes + (size_t)s * a.rounds_max * kBoxRoundFloats;
-    const int n = a.n_pts ? a.n_pts[s] : a.n_stride;
-    if (tid == 0) {
-      make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &sm.cam);
-      const int rc = lm_begin<P>(sm.lm, a.init + (size_t)prob * 4, a.lb, a.ub, a.max_iter);
-      sm.go = rc;
-      if (rc == LM_EVAL) { make_pose<P>(sm.lm.xt, &sm.pose); make_class(sm.pose, sm.cam, &sm.cls); }
-    }
-    const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);   // overlaps thread 0's set-up
-    __syncthreads();
-    while (sm.go == LM_EVAL) {
-      evaluate_cloud<CT, P>(sm, xyz_s, lab_s, pk_s, a.n_stride, n, box_s, resident, box_phase, gphase);
-      if (tid == 0) {
-        const int rc = lm_consume<P>(sm.lm, sm.tot);
-        sm.go = rc;
-        if (rc == LM_EVAL) { make_pose<P>(sm.lm.xt, &sm.pose); make_class(sm.pose, sm.cam, &sm.cls); }
+      if (q >= total) {
+        state = ST_IDLE;
+        if (lane == 0) { atomicSub(&sm.n_active, 1); atomicMin(tl + 1, global_ns()); }
+        continue;
       }
-      __syncthreads();
+      const int per_chunk = a.chunk * a.I;
+      const int c = q / per_chunk, within = q - c * per_chunk;
+      const int s0 = c * a.chunk;
+      const int gc = min(a.chunk, a.S - s0);             // samples in this chunk
+      const int rk = within / gc, s = s0 + (within - rk * gc);
+      const int prob = s * a.I + a.perm[(size_t)s * a.I + rk];
+      int rc = LM_DONE;
+      if (lane == 0) {
+        const int n = a.n_pts ? a.n_pts[s] : a.n_stride;
+        const int rounds = box_rounds(n);
+        const int len = slice_len(rounds, a.slice_rounds);
+        me.prob = prob;
+        me.pk = reinterpret_cast<const Entry<CT>*>(a.packed) + (size_t)s * a.rounds_max * kRoundPoints;
+        me.box = a.boxes + (size_t)s * a.rounds_max * kBoxRoundFloats;
+        me.rounds = rounds;
+        me.slice_rounds = len;
+        me.nslices = rounds > 0 ? (rounds + len - 1) / len : 1;    // an empty cloud still has one (empty) slice
+        make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &me.cam);
+        rc = lm_begin<P>(me.lm, a.init + (size_t)prob * 4, a.lb, a.ub, a.max_iter);
+        n_rec = 0;
+        if (rc == LM_EVAL) { make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls); open_pass<CT, P>(sm, me, warp); }
+      }
+      __syncwarp();                                     // lane 0's problem set-up is visible to the whole warp
+      rc = __shfl_sync(0xffffffffu, rc, 0);
+      state = (rc == LM_EVAL) ? ST_RUN : ST_FETCH;        // lm_begin always asks for an evaluation today
+      continue;
     }
-    if (tid == 0) {
-      const LMState<P>& st = sm.lm;
-      double* po = a.params_all + (size_t)prob * 6;
-      for (int j = 0; j < 6; ++j) po[j] = (j < P) ? st.x[j] : 0.0;
-      a.cost_all[prob] = st.cost;
-      int32_t* so = a.stats_all + (size_t)prob * 4;
-      so[0] = st.iteration; so[1] = st.evals; so[2] = st.ls_steps; so[3] = st.term;
+
+    // ---- pick a slice: one of mine first, else one of a CTA-mate's open pass ----
+    int owner = -1, k = 0, r_begin = 0, r_end = 0;
+    if (state == ST_RUN) {
+      int mine = -1, complete = 0;
+      if (lane == 0) {
+        const int ns = me.nslices;
+        if (ld_volatile(&me.next_slice) < ns) {
+          const int kk = atomicAdd(&me.next_slice, 1);
+          if (kk < ns) {
+            mine = kk;
+            if (kk == ns - 1) atomicAnd(&sm.open_mask, ~(1u << warp));
+          }
+        }
+        if (mine < 0 && ld_volatile(&me.done) == ns) complete = 1;
+      }
+      mine = __shfl_sync(0xffffffffu, mine, 0);
+      complete = __shfl_sync(0xffffffffu, complete, 0);
+      if (mine >= 0) {
+        owner = warp; k = mine;
+      } else if (complete) {
+        // every slice of my pass is in: add the slice sums in slice order, then lane 0 takes the control step
+        __threadfence_block();
+        const int ns = me.nslices;
+        if (lane < N) {
+          double v = me.part[0][lane];
+          for (int j = 1; j < ns; ++j) v += me.part[j][lane];
+          me.tot[lane] = v;
+        }
+        __syncwarp();
+        int rc = LM_DONE;
+        if (lane == 0) {
+          trace_record<CT, P>(a, me, n_rec, false);
+          rc = lm_consume<P>(me.lm, me.tot, &me.part[0][0]);
+          trace_record<CT, P>(a, me, n_rec, true);
+          ++n_rec;
+          if (rc == LM_EVAL) {
+            make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls);
+            open_pass<CT, P>(sm, me, warp);
+          } else {
+            const LMState<P>& st = me.lm;
+            double* po = a.params_all + (size_t)me.prob * 6;
+            for (int j = 0; j < 6; ++j) po[j] = (j < P) ? st.x[j] : 0.0;
+            a.cost_all[me.prob] = st.cost;
+            int32_t* so = a.stats_all + (size_t)me.prob * 4;
+            so[0] = st.iteration; so[1] = st.evals; so[2] = st.ls_steps; so[3] = st.term;
+          }
+        }
+        __syncwarp();
+        rc = __shfl_sync(0xffffffffu, rc, 0);
+        if (rc != LM_EVAL) state = ST_FETCH;
+        continue;
+      }
     }
-    __syncthreads();
+    if (owner < 0) {
+      // nothing of mine to do right now (idle, or waiting for helpers to finish my pass): help a CTA-mate
+      int o = -1, kk = 0;
+      if (lane == 0) {
+        const unsigned m = ld_volatile(&sm.open_mask) & ~(1u << warp);
+        if (m) {
+          const int cand = __ffs(m) - 1;
+          ProbCtx<CT, P>& oc = sm.ctx[cand];
+          if (ld_volatile(&oc.next_slice) < ld_volatile(&oc.nslices)) {
+            const int got = atomicAdd(&oc.next_slice, 1);
+            __threadfence_block();
+            const int ns = ld_volatile(&oc.nslices);      // re-read after the claim: the pass cannot change under a valid claim
+            if (got < ns) {
+              o = cand; kk = got;
+              if (got == ns - 1) atomicAnd(&sm.open_mask, ~(1u << cand));
+            }
+          }
+        }
+      }
+      __syncwarp();
+      o = __shfl_sync(0xffffffffu, o, 0);
+      kk = __shfl_sync(0xffffffffu, kk, 0);
+      if (o < 0) {
+        if (state == ST_IDLE) {
+          int na = 0;
+          if (lane == 0) na = ld_volatile(&sm.n_active);
+          na = __shfl_sync(0xffffffffu, na, 0);
+          if (na == 0) {                         // every problem of this CTA is finished
+            if (lane == 0) atomicMax(tl + 2, global_ns());
+            break;
+          }
+        }
+        __nanosleep(state == ST_IDLE ? 400 : 100);
+        continue;
+      }
+      owner = o; k = kk;
+    }
+    ProbCtx<CT, P>& oc = sm.ctx[owner];
+    {
+      const int len = oc.slice_rounds, rounds = oc.rounds;
+      r_begin = k * len;
+      r_end = min(rounds, r_begin + len);
+      if (r_begin > r_end) r_begin = r_end;
+    }
+    eval_slice<CT, P>(ws, oc, r_begin, r_end, oc.part[k], lane);
+    if (lane == 0) {
+      __threadfence_block();                      // part[k] before the completion count
+      atomicAdd(&oc.done, 1);
+    }
   }
 }
 
@@ -1704,10 +1557,17 @@ __device__ void pose_matrix(const double* x, int P, double* M) {
 }
 
 // Per-sample arg-min over inits (lowest index wins ties; NaN never wins) + pose matrix.
+// degenerate (may be NULL): samples without a predicted-inside point get P = I, cost = 1e4 (registration_lsq.py:329-332).
 __global__ void frustum_finalize_kernel(const double* params_all, const double* cost_all, int S, int I, int P,
-                                        double* P16_out, double* cost_out, int32_t* best_out) {
+                                        const int32_t* degenerate, double* P16_out, double* cost_out, int32_t* best_out) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= S) return;
+  if (degenerate && degenerate[s]) {
+    for (int j = 0; j < 16; ++j) P16_out[(size_t)s * 16 + j] = (j % 5 == 0) ? 1.0 : 0.0;
+    cost_out[s] = 1e4;
+    if (best_out) best_out[s] = 0;
+    return;
+  }
   int best = 0;
   double bc = cost_all[(size_t)s * I];
   if (!(bc == bc)) bc = INFINITY;
@@ -1720,41 +1580,64 @@ __global__ void frustum_finalize_kernel(const double* params_all, const double* 
   if (best_out) best_out[s] = best;
 }
 
+// One evaluation pass per sample (test hook and residual-free cost/gradient API): a CTA of kEvalWarps warps takes
+// the slices of the sample's pass round-robin and adds the slice sums in slice order -- the same slices, the same
+// per-slice arithmetic and the same order as inside the solver, so the totals are bit-identical to the solver's.
+constexpr int kEvalWarps = 4;
+
 template <typename CT, int P>
-__global__ void __launch_bounds__(kThreads) frustum_evaluate_kernel(const CT* xyz, const int8_t* label,
-                                                                     const int32_t* n_pts, int n_stride,
-                                                                     const double* K9, const double* x, double H,
-                                                                     double W, const float* boxes,
-                                                                     const Entry<CT>* packed, int rounds_max,
-                                                                     double* cost_out, double* grad_out,
-                                                                     double* JtJ_out) {
+struct EvalSmem {
+  WarpScratch<CT, P> scratch[kEvalWarps];
+  ProbCtx<CT, P> ctx;
+};
+
+template <typename CT, int P>
+__global__ void __launch_bounds__(kEvalWarps * 32) frustum_evaluate_kernel(const int32_t* n_pts, int n_stride,
+                                                                           const double* K9, const double* x, double H,
+                                                                           double W, const float* boxes,
+                                                                           const Entry<CT>* packed, int rounds_max,
+                                                                           int slice_rounds, double* cost_out,
+                                                                           double* grad_out, double* JtJ_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  Smem<CT, P>& sm = *reinterpret_cast<Smem<CT, P>*>(smem_raw);
-  const int tid = threadIdx.x;
+  EvalSmem<CT, P>& sm = *reinterpret_cast<EvalSmem<CT, P>*>(smem_raw);
+  constexpr int N = NAcc<P>::N;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int s = blockIdx.x;
+  ProbCtx<CT, P>& pb = sm.ctx;
   if (tid == 0) {
-    mbar_init(&sm.full, 1);
-    for (int w = 0; w < kWarps; ++w) { mbar_init(&sm.gbar[w][0], 1); mbar_init(&sm.gbar[w][1], 1); }
-    mbar_fence_init();
-    make_cam(K9 + (size_t)s * 9, H, W, &sm.cam);
-    make_pose<P>(x + (size_t)s * 6, &sm.pose);
-    make_class(sm.pose, sm.cam, &sm.cls);
+    const int n = n_pts ? n_pts[s] : n_stride;
+    const int rounds = box_rounds(n);
+    const int len = slice_len(rounds, slice_rounds);
+    pb.pk = packed + (size_t)s * rounds_max * kRoundPoints;
+    pb.box = boxes + (size_t)s * rounds_max * kBoxRoundFloats;
+    pb.rounds = rounds;
+    pb.slice_rounds = len;
+    pb.nslices = rounds > 0 ? (rounds + len - 1) / len : 1;
+    make_cam(K9 + (size_t)s * 9, H, W, &pb.cam);
+    make_pose<P>(x + (size_t)s * 6, &pb.pose);
+    make_class(pb.pose, pb.cam, &pb.cls);
   }
   __syncthreads();
-  uint32_t box_phase = 0, gphase = 0;
-  const int n = n_pts ? n_pts[s] : n_stride;
-  const float* box_s = boxes + (size_t)s * rounds_max * kBoxRoundFloats;
-  const bool resident = load_boxes<CT, P>(sm, box_s, n, box_phase);
+  const int ns = pb.nslices, len = pb.slice_rounds, rounds = pb.rounds;
+  for (int k = warp; k < ns; k += kEvalWarps) {
+    int r_begin = k * len, r_end = min(rounds, r_begin + len);
+    if (r_begin > r_end) r_begin = r_end;
+    eval_slice<CT, P>(sm.scratch[warp], pb, r_begin, r_end, pb.part[k], lane);
+  }
   __syncthreads();
-  evaluate_cloud<CT, P>(sm, xyz + (size_t)s * 3 * n_stride, label + (size_t)s * n_stride,
-                        packed + (size_t)s * rounds_max * (kThreads * 32), n_stride, n, box_s, resident, box_phase, gphase);
+  if (tid < N) {
+    double v = pb.part[0][tid];
+    for (int j = 1; j < ns; ++j) v += pb.part[j][tid];
+    pb.tot[tid] = v;
+  }
+  __syncthreads();
   if (tid == 0) {
-    cost_out[s] = sm.tot[0];
-    for (int j = 0; j < 6; ++j) grad_out[(size_t)s * 6 + j] = (j < P) ? sm.tot[1 + j] : 0.0;
+    cost_out[s] = pb.tot[0];
+    for (int j = 0; j < 6; ++j) grad_out[(size_t)s * 6 + j] = (j < P) ? pb.tot[1 + j] : 0.0;
     for (int j = 0; j < 36; ++j) JtJ_out[(size_t)s * 36 + j] = 0.0;
     for (int j = 0; j < P; ++j)
       for (int k = 0; k < P; ++k)
-        JtJ_out[(size_t)s * 36 + j * P + k] = sm.tot[1 + P + (j <= k ? tri(P, j, k) : tri(P, k, j))];
+        JtJ_out[(size_t)s * 36 + j * P + k] = pb.tot[1 + P + (j <= k ? tri(P, j, k) : tri(P, k, j))];
   }
 }
 
@@ -1790,12 +1673,16 @@ static size_t box_table_bytes(int S, int n_stride) {
 }
 // packed per-launch copy of the clouds; sized for the wider (f64) record so one workspace serves both ABIs
 static size_t packed_bytes(int S, int n_stride) {
-#if DIB_PACKED
-  return align_up((size_t)(S > 0 ? S : 0) * box_rounds(n_stride) * (kThreads * 32) * sizeof(Entry<double>), 256);
-#else
-  (void)S; (void)n_stride;
-  return 0;
-#endif
+  return align_up((size_t)(S > 0 ? S : 0) * box_rounds(n_stride) * kRoundPoints * sizeof(Entry<double>), 256);
+}
+
+static int default_slice_rounds() {
+  static const int v = [] {
+    const char* e = getenv("DIB_SLICE_ROUNDS");          // tuning knob; results depend on it at rounding level only
+    const int x = e ? atoi(e) : DIB_SLICE_ROUNDS;
+    return x < 1 ? 1 : x;
+  }();
+  return v;
 }
 
 template <typename CT>
@@ -1804,7 +1691,7 @@ static int launch_boxes(const CT* xyz, const int8_t* label, const int32_t* n_pts
   const int rounds_max = box_rounds(n_stride);
   if (rounds_max == 0 || S == 0) return DIB_OK;
   DIB_REQUIRE(S <= 65535, "S (%d) exceeds grid.y; split the batch", S);
-  const int groups = rounds_max * kThreads;
+  const int groups = rounds_max * kRoundGroups;
   dim3 grid((groups + 7) / 8, S);
   frustum_boxes_kernel<CT><<<grid, 256, 0, st>>>(xyz, label, n_pts, n_stride, rounds_max, table, packed);
   DIB_CHECK_CUDA(cudaGetLastError());
@@ -1820,28 +1707,50 @@ static int check_cloud_args(const CT* xyz, const int8_t* label, int n_stride, in
   return DIB_OK;
 }
 
+// Optional CUDA events recorded right before / after the solve kernel on its launch stream (dib_profile_solve_events):
+// lets a benchmark time the dominant kernel INSIDE its timed steps instead of in a separate loop.
+static thread_local void* g_ev_start = nullptr;
+static thread_local void* g_ev_stop = nullptr;
+
+// Per-device launch configuration of a solver instantiation, looked up once (cudaFuncSetAttribute and the
+// occupancy query cost tens of microseconds per call, which the single-problem drop-in path would pay every time).
+struct LaunchCfg { int sms = 0, per_sm = 0; };
+template <typename CT, int P>
+static int solver_launch_cfg(LaunchCfg* out) {
+  static LaunchCfg cache[64];
+  int dev = 0;
+  DIB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && cache[dev].per_sm > 0) { *out = cache[dev]; return DIB_OK; }
+  auto kern = frustum_solve_kernel<CT, P>;
+  const size_t smem = sizeof(Smem<CT, P>);
+  LaunchCfg c;
+  DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DIB_CHECK_CUDA(cudaDeviceGetAttribute(&c.sms, cudaDevAttrMultiProcessorCount, dev));
+  DIB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c.per_sm, kern, Cfg<CT, P>::kWarps * 32, smem));
+  if (c.per_sm < 1) { set_error("solver kernel does not fit an SM (%zu B shared memory)", smem); return DIB_ECUDA; }
+  if (dev >= 0 && dev < 64) cache[dev] = c;
+  *out = c;
+  return DIB_OK;
+}
+
 template <typename CT, int P>
 static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   SolveArgs a = a_in;
-  auto kern = frustum_solve_kernel<CT, P>;
-  const size_t smem = sizeof(Smem<CT, P>);
-  DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int dev = 0, sms = 0, per_sm = 0;
-  DIB_CHECK_CUDA(cudaGetDevice(&dev));
-  DIB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  DIB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-  if (per_sm < 1) per_sm = 1;
-  long long grid = (long long)sms * per_sm;
+  LaunchCfg cfg;
+  const int rc = solver_launch_cfg<CT, P>(&cfg);
+  if (rc != DIB_OK) return rc;
+  constexpr int kW = Cfg<CT, P>::kWarps;
   const long long total = (long long)a.S * a.I;
+  if (total < 1) return DIB_OK;
+  // One CTA (a team of kW warps, one problem per warp) per SM.  A batch with fewer problems than warps is spread
+  // one problem per CTA first (the kernel deals the first wave rank-major), so the spare warps of every CTA help.
+  long long grid = (long long)cfg.sms * cfg.per_sm;
   if (grid > total) grid = total;
-  if (grid < 1) return DIB_OK;
   // scheduling chunk: as many samples as keep the concurrently touched clouds around 32 MB (a quarter of
-  // L2), and at least ~2x the resident problems.  Measured on B200 (512 x 60 problems): 1 or 50 samples
+  // L2), and at least ~2x the resident problems.  Measured on B200 (512 x 60 problems, round 1): 1 or 50 samples
   // 103.3 ms, 128 samples 97.7 ms, 256 samples 99.8 ms, 512 samples (no chunking) ~100 ms.
-  long long chunk = (2 * grid + a.I - 1) / a.I;
-  const long long bytes_per_sample =
-      DIB_PACKED ? (long long)a.rounds_max * (kThreads * 32) * (long long)sizeof(Entry<CT>)
-                 : (long long)a.n_stride * (3 * (long long)sizeof(CT) + 1);
+  long long chunk = (2 * grid * kW + a.I - 1) / a.I;
+  const long long bytes_per_sample = (long long)a.rounds_max * kRoundPoints * (long long)sizeof(Entry<CT>);
   if (bytes_per_sample > 0 && chunk < (32ll << 20) / bytes_per_sample) chunk = (32ll << 20) / bytes_per_sample;
   if (const char* e = getenv("DIB_CHUNK_SAMPLES")) chunk = atoll(e);   // tuning knob
   if (chunk < 1) chunk = 1;
@@ -1852,29 +1761,38 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
     chunk = (a.S + nchunks - 1) / nchunks;
   }
   a.chunk = (int)chunk;
-  // (Queueing the top 4 / 10 longest-predicted inits of EVERY sample ahead of the chunked walk measured
-  // 1 % / 3 % slower: the tail comes from mispredicted long solves, not from the predicted ones.)
-  kern<<<(unsigned)grid, kThreads, smem, st>>>(a);
+  if (g_ev_start) DIB_CHECK_CUDA(cudaEventRecord((cudaEvent_t)g_ev_start, st));
+  frustum_solve_kernel<CT, P><<<(unsigned)grid, kW * 32, sizeof(Smem<CT, P>), st>>>(a);
   DIB_CHECK_CUDA(cudaGetLastError());
+  if (g_ev_stop) DIB_CHECK_CUDA(cudaEventRecord((cudaEvent_t)g_ev_stop, st));
   return DIB_OK;
+}
+
+static size_t solve_workspace_bytes_impl(int S, int I, int n_stride) {
+  const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
+  return 256 + align_up(n * 6 * sizeof(double), 256) + align_up(n * sizeof(double), 256) +
+         align_up(n * 4 * sizeof(int32_t), 256) + box_table_bytes(S, n_stride > 0 ? n_stride : 0) +
+         packed_bytes(S, n_stride > 0 ? n_stride : 0) + align_up(n * sizeof(int32_t), 256);
 }
 
 template <typename CT>
 static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
                        const double* init, const double* lb3, const double* ub3, double H, double W, int max_iter,
                        int is_2d, int S, int I, double* P16_out, double* cost_out, int32_t* best_out,
-                       double* params_all, double* cost_all, int32_t* stats_all, void* workspace,
-                       size_t workspace_bytes, dib_stream_t stream) {
+                       double* params_all, double* cost_all, int32_t* stats_all, const int32_t* degenerate,
+                       double* trace, int trace_cap, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
   int rc = check_cloud_args<CT>(xyz, label, n_stride, S);
   if (rc != DIB_OK) return rc;
   DIB_REQUIRE(I >= 1, "I must be >= 1");
   DIB_REQUIRE(K9 && init && lb3 && ub3 && P16_out && cost_out, "NULL argument");
-  DIB_REQUIRE((long long)S * I < (1ll << 31), "S*I too large");
+  DIB_REQUIRE((long long)S * I < (1ll << 30), "S*I too large");
+  DIB_REQUIRE(trace == nullptr || trace_cap >= 1, "trace_cap must be >= 1");
   if (S == 0) return DIB_OK;
-  if (workspace_bytes < frustum_solve_workspace_bytes(S, I, n_stride) || workspace == nullptr) {
-    set_error("workspace too small: %zu < %zu", workspace_bytes, frustum_solve_workspace_bytes(S, I, n_stride));
+  if (workspace_bytes < solve_workspace_bytes_impl(S, I, n_stride) || workspace == nullptr) {
+    set_error("workspace too small: %zu < %zu", workspace_bytes, solve_workspace_bytes_impl(S, I, n_stride));
     return DIB_ENOMEM;
   }
+  DIB_REQUIRE(((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   unsigned char* ws = (unsigned char*)workspace;
   const size_t n = (size_t)S * I;
@@ -1889,7 +1807,7 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   off += align_up(n * 4 * sizeof(int32_t), 256);
   float* table = (float*)(ws + off);
   off += box_table_bytes(S, n_stride);
-  Entry<CT>* packed = DIB_PACKED ? (Entry<CT>*)(ws + off) : nullptr;
+  Entry<CT>* packed = (Entry<CT>*)(ws + off);
   off += packed_bytes(S, n_stride);
   int32_t* perm = (int32_t*)(ws + off);
   a.boxes = table;
@@ -1899,7 +1817,12 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   a.xyz = xyz; a.label = label; a.n_pts = n_pts; a.n_stride = n_stride; a.K9 = K9; a.init = init;
   for (int k = 0; k < 3; ++k) { a.lb[k] = lb3[k]; a.ub[k] = ub3[k]; }
   a.H = H; a.W = W; a.max_iter = max_iter; a.S = S; a.I = I;
+  a.chunk = 1;
+  a.slice_rounds = default_slice_rounds();
+  a.trace = trace; a.trace_cap = trace_cap;
   DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
+  DIB_CHECK_CUDA(cudaMemsetAsync((unsigned char*)a.queue + 8, 0xff, 16, st));   // timeline minima start at ~0ull
+  if (trace) DIB_CHECK_CUDA(cudaMemsetAsync(trace, 0, n * (size_t)trace_cap * kTraceRec * sizeof(double), st));
   rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, packed, st);
   if (rc != DIB_OK) return rc;
   {
@@ -1910,8 +1833,27 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   }
   rc = is_2d ? launch_solve<CT, 4>(a, st) : launch_solve<CT, 6>(a, st);
   if (rc != DIB_OK) return rc;
-  frustum_finalize_kernel<<<(S + 127) / 128, 128, 0, st>>>(a.params_all, a.cost_all, S, I, is_2d ? 4 : 6, P16_out,
-                                                          cost_out, best_out);
+  frustum_finalize_kernel<<<(S + 127) / 128, 128, 0, st>>>(a.params_all, a.cost_all, S, I, is_2d ? 4 : 6, degenerate,
+                                                          P16_out, cost_out, best_out);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+template <typename CT, int P>
+static int launch_evaluate(const int32_t* n_pts, int n_stride, const double* K9, const double* x, double H, double W,
+                           int S, const float* table, const Entry<CT>* packed, double* cost_out, double* grad_out,
+                           double* JtJ_out, cudaStream_t st) {
+  auto kern = frustum_evaluate_kernel<CT, P>;
+  const size_t smem = sizeof(EvalSmem<CT, P>);
+  static bool configured[64] = {};
+  int dev = 0;
+  DIB_CHECK_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  kern<<<S, kEvalWarps * 32, smem, st>>>(n_pts, n_stride, K9, x, H, W, table, packed, box_rounds(n_stride),
+                                         default_slice_rounds(), cost_out, grad_out, JtJ_out);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }
@@ -1928,27 +1870,14 @@ static int evaluate_batch(const CT* xyz, const int8_t* label, const int32_t* n_p
     set_error("workspace too small: %zu < %zu", workspace_bytes, frustum_evaluate_workspace_bytes(S, n_stride));
     return DIB_ENOMEM;
   }
+  DIB_REQUIRE(((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   float* table = (float*)workspace;
-  Entry<CT>* packed = DIB_PACKED ? (Entry<CT>*)((unsigned char*)workspace + box_table_bytes(S, n_stride)) : nullptr;
-  const int rounds_max = box_rounds(n_stride);
+  Entry<CT>* packed = (Entry<CT>*)((unsigned char*)workspace + box_table_bytes(S, n_stride));
   rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, packed, st);
   if (rc != DIB_OK) return rc;
-  if (is_2d) {
-    auto kern = frustum_evaluate_kernel<CT, 4>;
-    const size_t smem = sizeof(Smem<CT, 4>);
-    DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, packed, rounds_max, cost_out,
-                                    grad_out, JtJ_out);
-  } else {
-    auto kern = frustum_evaluate_kernel<CT, 6>;
-    const size_t smem = sizeof(Smem<CT, 6>);
-    DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<S, kThreads, smem, st>>>(xyz, label, n_pts, n_stride, K9, x, H, W, table, packed, rounds_max, cost_out,
-                                    grad_out, JtJ_out);
-  }
-  DIB_CHECK_CUDA(cudaGetLastError());
-  return DIB_OK;
+  return is_2d ? launch_evaluate<CT, 4>(n_pts, n_stride, K9, x, H, W, S, table, packed, cost_out, grad_out, JtJ_out, st)
+               : launch_evaluate<CT, 6>(n_pts, n_stride, K9, x, H, W, S, table, packed, cost_out, grad_out, JtJ_out, st);
 }
 
 template <typename CT>
@@ -1968,66 +1897,17 @@ static int residuals_single(const CT* xyz, const int8_t* label, int n, int n_str
   return DIB_OK;
 }
 
-static size_t solve_workspace_bytes_impl(int S, int I, int n_stride) {
-  const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
-  return 256 + align_up(n * 6 * sizeof(double), 256) + align_up(n * sizeof(double), 256) +
-         align_up(n * 4 * sizeof(int32_t), 256) + box_table_bytes(S, n_stride > 0 ? n_stride : 0) +
-         packed_bytes(S, n_stride > 0 ? n_stride : 0) + align_up(n * sizeof(int32_t), 256);
-}
-
-#if DIB_WIDE_TU
-// Entry points of the wide (128-thread CTA) build of this file; called by the primary TU's C ABI for
-// batches with few problems (a problem then finishes ~1.8x sooner and the persistent grid balances better).
-size_t wide_solve_workspace_bytes(int S, int I, int n_stride) { return solve_workspace_bytes_impl(S, I, n_stride); }
-int wide_solve_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
-                   const double* init, const double* lb3, const double* ub3, double H, double W, int max_iter, int is_2d,
-                   int S, int I, double* P16_out, double* cost_out, int32_t* best_out, double* params_all,
-                   double* cost_all, int32_t* stats_all, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
-  return solve_batch<float>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
-                            cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
-}
-int wide_solve_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
-                   const double* init, const double* lb3, const double* ub3, double H, double W, int max_iter, int is_2d,
-                   int S, int I, double* P16_out, double* cost_out, int32_t* best_out, double* params_all,
-                   double* cost_all, int32_t* stats_all, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
-  return solve_batch<double>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
-                             cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
-}
-#endif
-
 }  // namespace dib
-
-#if !DIB_WIDE_TU
-#ifndef DIB_HAVE_WIDE
-#define DIB_HAVE_WIDE 0                       // set by the build when frustum_solver_wide.cu is linked in
-#endif
-#if DIB_HAVE_WIDE
-namespace dib_w128 {
-size_t wide_solve_workspace_bytes(int S, int I, int n_stride);
-int wide_solve_f32(const float*, const int8_t*, const int32_t*, int, const double*, const double*, const double*,
-                   const double*, double, double, int, int, int, int, double*, double*, int32_t*, double*, double*,
-                   int32_t*, void*, size_t, dib_stream_t);
-int wide_solve_f64(const double*, const int8_t*, const int32_t*, int, const double*, const double*, const double*,
-                   const double*, double, double, int, int, int, int, double*, double*, int32_t*, double*, double*,
-                   int32_t*, void*, size_t, dib_stream_t);
-}  // namespace dib_w128
-#endif
-// Batches with fewer than DIB_WIDE_BELOW problems (S x I) go to the 128-thread build.  Experimental: the
-// default 0 never does (not yet measured on a B200; scripts/round2_sweep.sh).
-static bool use_wide(int S, int I) {
-#if DIB_HAVE_WIDE
-  static const long long below = getenv("DIB_WIDE_BELOW") ? atoll(getenv("DIB_WIDE_BELOW")) : 0;
-  return (long long)S * I < below;
-#else
-  (void)S; (void)I;
-  return false;
-#endif
-}
 
 extern "C" {
 
-int dib_abi_version(void) { return 2; }
+int dib_abi_version(void) { return 3; }
 const char* dib_last_error(void) { return dib::g_err; }
+
+void dib_profile_solve_events(void* start_event, void* stop_event) {
+  dib::g_ev_start = start_event;
+  dib::g_ev_stop = stop_event;
+}
 
 int dib_device_sm_count(void) {
   int dev = 0, sms = 0;
@@ -2036,14 +1916,7 @@ int dib_device_sm_count(void) {
   return sms;
 }
 
-size_t frustum_solve_workspace_bytes(int S, int I, int n_stride) {
-  size_t need = dib::solve_workspace_bytes_impl(S, I, n_stride);
-#if DIB_HAVE_WIDE
-  const size_t wide = dib_w128::wide_solve_workspace_bytes(S, I, n_stride);
-  if (wide > need) need = wide;
-#endif
-  return need;
-}
+size_t frustum_solve_workspace_bytes(int S, int I, int n_stride) { return dib::solve_workspace_bytes_impl(S, I, n_stride); }
 
 size_t frustum_evaluate_workspace_bytes(int S, int n_stride) {
   return dib::box_table_bytes(S, n_stride > 0 ? n_stride : 0) + dib::packed_bytes(S, n_stride > 0 ? n_stride : 0) + 256;
@@ -2054,14 +1927,9 @@ int frustum_solve_batch_f32(const float* xyz, const int8_t* label, const int32_t
                             double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
                             int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
                             void* workspace, size_t workspace_bytes, dib_stream_t stream) {
-#if DIB_HAVE_WIDE
-  if (use_wide(S, I))
-    return dib_w128::wide_solve_f32(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
-                                    cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
-#endif
   return dib::solve_batch<float>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
-                                 P16_out, cost_out, best_out, params_all, cost_all, stats_all, workspace,
-                                 workspace_bytes, stream);
+                                 P16_out, cost_out, best_out, params_all, cost_all, stats_all, nullptr, nullptr, 0,
+                                 workspace, workspace_bytes, stream);
 }
 
 int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
@@ -2069,14 +1937,74 @@ int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_
                             double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
                             int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
                             void* workspace, size_t workspace_bytes, dib_stream_t stream) {
-#if DIB_HAVE_WIDE
-  if (use_wide(S, I))
-    return dib_w128::wide_solve_f64(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
-                                    cost_out, best_out, params_all, cost_all, stats_all, workspace, workspace_bytes, stream);
-#endif
   return dib::solve_batch<double>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
-                                  P16_out, cost_out, best_out, params_all, cost_all, stats_all, workspace,
-                                  workspace_bytes, stream);
+                                  P16_out, cost_out, best_out, params_all, cost_all, stats_all, nullptr, nullptr, 0,
+                                  workspace, workspace_bytes, stream);
+}
+
+int frustum_solve_traced_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                             const double* K9, const double* init, const double* lb3, const double* ub3, double H,
+                             double W, int max_iter, int is_2d, int S, int I, double* P16_out, double* cost_out,
+                             int32_t* best_out, double* params_all, double* cost_all, int32_t* stats_all,
+                             double* trace, int trace_cap, void* workspace, size_t workspace_bytes,
+                             dib_stream_t stream) {
+  DIB_REQUIRE(trace != nullptr, "trace must not be NULL");
+  return dib::solve_batch<float>(xyz, label, n_pts, n_stride, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I,
+                                 P16_out, cost_out, best_out, params_all, cost_all, stats_all, nullptr, trace,
+                                 trace_cap, workspace, workspace_bytes, stream);
+}
+
+// Whole per-sample body of registration_lsq.py:329-343 in one call: initial guess + front filter + perturbed inits
+// (frustum_prepare_batch_f32), the multi-start solve, the arg-min and the degenerate-sample rule.
+static size_t register_front_bytes(int S, int I, int n_in, size_t off[6]) {
+  const size_t Ns = (size_t)((n_in > 0 ? n_in : 0) + 15) & ~(size_t)15;
+  const size_t s = (size_t)(S > 0 ? S : 0), i = (size_t)(I > 0 ? I : 0);
+  size_t o = 0;
+  off[0] = o; o += dib::align_up(s * 3 * Ns * sizeof(float), 256);      // xyz
+  off[1] = o; o += dib::align_up(s * Ns, 256);                          // label
+  off[2] = o; o += dib::align_up(s * sizeof(int32_t), 256);             // n_pts
+  off[3] = o; o += dib::align_up(s * i * 4 * sizeof(double), 256);      // init
+  off[4] = o; o += dib::align_up(s * sizeof(double), 256);              // init_y_angle
+  off[5] = o; o += dib::align_up(s * sizeof(int32_t), 256);             // degenerate
+  return o;
+}
+
+size_t frustum_register_workspace_bytes(int S, int I, int n_in) {
+  size_t off[6];
+  const int Ns = ((n_in > 0 ? n_in : 0) + 15) & ~15;
+  return register_front_bytes(S, I, n_in, off) + dib::solve_workspace_bytes_impl(S, I, Ns);
+}
+
+int frustum_register_batch_f32(const float* xyz_in, const int8_t* pred, int n_in, int n_in_stride, int S, int I,
+                               uint64_t seed, double ry_sigma, double t_amp, const double* K9, const double* lb3,
+                               const double* ub3, double H, double W, int max_iter, int is_2d, double* P16_out,
+                               double* cost_out, int32_t* best_out, double* init_y_angle_out, int32_t* n_pts_out,
+                               int32_t* degenerate_out, double* init_out, double* params_all, double* cost_all,
+                               int32_t* stats_all, void* workspace, size_t workspace_bytes, dib_stream_t stream) {
+  DIB_REQUIRE(S >= 0 && I >= 1 && n_in >= 0, "bad sizes");
+  if (S == 0) return DIB_OK;
+  size_t off[6];
+  const size_t front = register_front_bytes(S, I, n_in, off);
+  const int Ns = (n_in + 15) & ~15;
+  const size_t need = front + dib::solve_workspace_bytes_impl(S, I, Ns);
+  if (workspace == nullptr || workspace_bytes < need) {
+    dib::set_error("workspace too small: %zu < %zu", workspace_bytes, need);
+    return DIB_ENOMEM;
+  }
+  DIB_REQUIRE(((uintptr_t)workspace % 256) == 0, "workspace must be 256-byte aligned");
+  unsigned char* ws = (unsigned char*)workspace;
+  float* xyz = (float*)(ws + off[0]);
+  int8_t* label = (int8_t*)(ws + off[1]);
+  int32_t* n_pts = n_pts_out ? n_pts_out : (int32_t*)(ws + off[2]);
+  double* init = init_out ? init_out : (double*)(ws + off[3]);
+  double* ang = init_y_angle_out ? init_y_angle_out : (double*)(ws + off[4]);
+  int32_t* degen = degenerate_out ? degenerate_out : (int32_t*)(ws + off[5]);
+  int rc = frustum_prepare_batch_f32(xyz_in, pred, n_in, n_in_stride, S, I, seed, ry_sigma, t_amp, 1, xyz, label, n_pts,
+                                     init, ang, degen, nullptr, 0, stream);
+  if (rc != DIB_OK) return rc;
+  return dib::solve_batch<float>(xyz, label, n_pts, Ns, K9, init, lb3, ub3, H, W, max_iter, is_2d, S, I, P16_out,
+                                 cost_out, best_out, params_all, cost_all, stats_all, degen, nullptr, 0, ws + front,
+                                 workspace_bytes - front, stream);
 }
 
 int frustum_evaluate_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride, const double* K9,
@@ -2105,4 +2033,3 @@ int frustum_residuals_f64(const double* xyz, const int8_t* label, int n, int n_s
 }
 
 }  // extern "C"
-#endif  // !DIB_WIDE_TU

@@ -83,6 +83,31 @@ def _as_K(K, S, device):
     return K.to(device)
 
 
+def _check_cloud(xyz, label=None, n_pts=None, what="xyz", dtypes=(torch.float32, torch.float64)):
+    """Shape / device / layout checks shared by every wrapper that hands raw pointers to the C ABI: a CPU tensor or a
+    sliced view would otherwise be read as if it were a contiguous device array."""
+    if not isinstance(xyz, torch.Tensor) or not xyz.is_cuda:
+        raise ValueError(f"{what} must be a CUDA tensor")
+    if xyz.dim() != 3 or xyz.shape[1] != 3:
+        raise ValueError(f"{what} must be [S,3,Ns]")
+    if xyz.dtype not in dtypes:
+        raise ValueError(f"{what} must be one of {dtypes}")
+    if not xyz.is_contiguous():
+        raise ValueError(f"{what} must be contiguous (a sliced view would be read with the wrong stride)")
+    S, _, Ns = xyz.shape
+    if Ns % 16 != 0:
+        raise ValueError("the point stride must be a multiple of 16 (pack_clouds pads)")
+    if label is not None:
+        if not (isinstance(label, torch.Tensor) and label.is_cuda and label.device == xyz.device):
+            raise ValueError("label must be a CUDA tensor on the same device")
+        if label.dtype != torch.int8 or tuple(label.shape) != (S, Ns) or not label.is_contiguous():
+            raise ValueError("label must be a contiguous int8 [S,Ns] tensor")
+    if n_pts is not None:
+        if not (isinstance(n_pts, torch.Tensor) and n_pts.numel() == S):
+            raise ValueError("n_pts must hold S entries")
+    return S, Ns
+
+
 _ws_cache = {}
 
 
@@ -97,8 +122,28 @@ def _workspace(nbytes, device, stream_ptr=0):
     return buf
 
 
+def last_solve_timeline(device=None, stream=None, register_shape=None):
+    """(start_ns, queue_empty_ns, end_ns) of the most recent solve launched with this (device, stream)'s workspace, read
+    from the timeline words the solver kernel writes next to its queue counter (globaltimer nanoseconds).  Benchmark
+    aid: end - queue_empty is the end-of-kernel tail during which SMs run out of problems.
+    register_shape = (S, I, n_in) when the last call was register_batch (the solver's block then sits behind the
+    front-filtered clouds in the workspace)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(_stream_ptr(stream)))
+    buf = _ws_cache.get(key)
+    if buf is None:
+        return None
+    off = 0
+    if register_shape is not None:
+        lib = _native.load()
+        S, I, n_in = (int(v) for v in register_shape)
+        off = lib.frustum_register_workspace_bytes(S, I, n_in) - lib.frustum_solve_workspace_bytes(S, I, round_up(n_in, 16))
+    w = buf[off:off + 32].cpu().numpy().view(np.uint64)
+    return int(w[1]), int(w[2]), int(w[3])
+
+
 def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB, max_iter=500,
-                is_2d=True, return_all=False, stream=None, out=None):
+                is_2d=True, return_all=False, stream=None, out=None, trace_cap=0):
     """Batched multi-start solve, everything resident on the device.
 
     xyz [S,3,Ns] f32|f64 cuda, label [S,Ns] int8 cuda, n_pts [S] int32 cuda or None,
@@ -107,18 +152,12 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
     = (LM iterations, cloud passes, line-search contractions, termination) if return_all).
     `out`: a dict returned by an earlier call with the same shapes; its tensors are overwritten in place
     (no allocation inside the call).
+    trace_cap > 0 (float32 record only): additionally returns trace [S,I,trace_cap,16] f64, one record per cloud
+    pass (layout: include/deepi2p_b200.h, frustum_solve_traced_f32) -- parity tooling.
     """
     _require_cuda()
     lib = _native.load()
-    if not (xyz.is_cuda and label.is_cuda):
-        raise ValueError("xyz/label must be CUDA tensors")
-    if xyz.dtype not in (torch.float32, torch.float64) or label.dtype != torch.int8:
-        raise ValueError("xyz must be float32/float64 and label int8")
-    if not (xyz.is_contiguous() and label.is_contiguous()):
-        raise ValueError("xyz/label must be contiguous")
-    S, three, Ns = xyz.shape
-    if three != 3 or tuple(label.shape) != (S, Ns):
-        raise ValueError("shape mismatch")
+    S, Ns = _check_cloud(xyz, label, n_pts)
     dev = xyz.device
     init = torch.as_tensor(init, dtype=torch.float64).to(dev).contiguous()
     if init.dim() != 3 or init.shape[0] != S or init.shape[2] != 4:
@@ -150,12 +189,24 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
         wsb = lib.frustum_solve_workspace_bytes(S, I, Ns)
         sp = _stream_ptr(stream)
         ws = _workspace(wsb, dev, sp)
-        fn = lib.frustum_solve_batch_f32 if xyz.dtype == torch.float32 else lib.frustum_solve_batch_f64
-        rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(init), lb.ctypes.data, ub.ctypes.data,
+        trace = None
+        if trace_cap > 0:
+            if xyz.dtype != torch.float32:
+                raise ValueError("the traced solve takes the float32 record")
+            trace = torch.empty((S, I, int(trace_cap), 16), dtype=torch.float64, device=dev)
+            rc = lib.frustum_solve_traced_f32(
+                _ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(init), lb.ctypes.data, ub.ctypes.data,
                 float(H), float(W), int(max_iter), 1 if is_2d else 0, S, I, _ptr(P), _ptr(cost), _ptr(best),
-                _ptr(params), _ptr(costs), _ptr(stats), _ptr(ws), ws.numel(), sp)
+                _ptr(params), _ptr(costs), _ptr(stats), _ptr(trace), int(trace_cap), _ptr(ws), ws.numel(), sp)
+        else:
+            fn = lib.frustum_solve_batch_f32 if xyz.dtype == torch.float32 else lib.frustum_solve_batch_f64
+            rc = fn(_ptr(xyz), _ptr(label), _ptr(n_pts), Ns, _ptr(K9), _ptr(init), lb.ctypes.data, ub.ctypes.data,
+                    float(H), float(W), int(max_iter), 1 if is_2d else 0, S, I, _ptr(P), _ptr(cost), _ptr(best),
+                    _ptr(params), _ptr(costs), _ptr(stats), _ptr(ws), ws.numel(), sp)
     _native.check(rc, "frustum_solve_batch")
     res = dict(P=P, cost=cost, best=best)
+    if trace is not None:
+        res["trace"] = trace
     if return_all:
         res.update(params=params, costs=costs, stats=stats)
     return res
@@ -165,9 +216,11 @@ def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None):
     """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook)."""
     _require_cuda()
     lib = _native.load()
-    S, _, Ns = xyz.shape
+    S, Ns = _check_cloud(xyz, label, n_pts)
     dev = xyz.device
     K9 = _as_K(K, S, dev)
+    if n_pts is not None:
+        n_pts = n_pts.to(dev, torch.int32).contiguous()
     x = torch.as_tensor(x, dtype=torch.float64).to(dev).contiguous().reshape(S, 6)
     with torch.cuda.device(dev):
         cost = torch.empty((S,), dtype=torch.float64, device=dev)
@@ -215,11 +268,11 @@ def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=
     n_pts, init, init_y_angle, degenerate) ready for solve_batch."""
     _require_cuda()
     lib = _native.load()
-    S, _, Ns_in = xyz_in.shape
+    S, Ns_in = _check_cloud(xyz_in, pred, what="xyz_in", dtypes=(torch.float32,))
     dev = xyz_in.device
-    if xyz_in.dtype != torch.float32 or pred.dtype != torch.int8:
-        raise ValueError("prepare_batch takes float32 coordinates and int8 predictions")
-    Ns = round_up(max(int(n_in), 1), 16)
+    if not (0 <= int(n_in) <= Ns_in):
+        raise ValueError("n_in must be within the point stride")
+    Ns = round_up(int(n_in), 16)             # exactly the C side's n_out_stride ((n_in + 15) & ~15); 0 for an empty cloud
     with torch.cuda.device(dev):
         xyz = torch.empty((S, 3, Ns), dtype=torch.float32, device=dev)
         label = torch.empty((S, Ns), dtype=torch.int8, device=dev)
@@ -236,20 +289,56 @@ def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=
 
 
 def register_batch(xyz_in, pred, n_in, K, H, W, n_inits=60, seed=0, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB,
-                   max_iter=500, is_2d=True, return_all=False, stream=None):
-    """Batched body of registration_lsq.py:329-343: initial guess, front filter, n_inits perturbed
-    starts, min-cost pose; degenerate samples (no predicted-inside point) get P = I, cost = 1e4."""
-    prep = prepare_batch(xyz_in, pred, n_in, n_inits, seed=seed, stream=stream)
-    out = solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K, prep["init"], H, W, t_lb, t_ub, max_iter,
-                      is_2d, return_all=return_all, stream=stream)
-    deg = prep["degenerate"].bool()
-    eye = torch.eye(4, dtype=torch.float64, device=out["P"].device)
-    out["P"] = torch.where(deg[:, None, None], eye, out["P"])
-    out["cost"] = torch.where(deg, torch.full_like(out["cost"], 1e4), out["cost"])
-    out["init_y_angle"] = prep["init_y_angle"]
-    out["n_pts"] = prep["n_pts"]
-    out["degenerate"] = prep["degenerate"]
-    return out
+                   max_iter=500, is_2d=True, return_all=False, stream=None, out=None):
+    """Batched body of registration_lsq.py:329-343 in ONE C-ABI call (frustum_register_batch_f32): initial guess,
+    front filter, n_inits perturbed starts, the multi-start solve, min-cost pose; degenerate samples (no
+    predicted-inside point) get P = I, cost = 1e4.  This is the call that replaces the reference's
+    fork-per-solve loop (registration_lsq.py:142-186).
+
+    xyz_in [S,3,Ns_in] f32 cuda, pred [S,Ns_in] int8 cuda, n_in valid points per cloud.  Returns dict(P [S,4,4],
+    cost [S], best [S], init_y_angle [S], n_pts [S], degenerate [S]) (+ init [S,I,4], params [S,I,6],
+    costs [S,I], stats [S,I,4] if return_all).  `out`: the dict of an earlier call with the same shapes; its
+    tensors are overwritten in place, so a steady-state loop allocates nothing."""
+    _require_cuda()
+    lib = _native.load()
+    S, Ns_in = _check_cloud(xyz_in, pred, what="xyz_in", dtypes=(torch.float32,))
+    dev = xyz_in.device
+    n_in, I = int(n_in), int(n_inits)
+    if not (0 <= n_in <= Ns_in) or I < 1:
+        raise ValueError("bad n_in / n_inits")
+    K9 = _as_K(K, S, dev)
+    lb = np.ascontiguousarray(np.asarray(t_lb, dtype=np.float64).reshape(3))
+    ub = np.ascontiguousarray(np.asarray(t_ub, dtype=np.float64).reshape(3))
+    with torch.cuda.device(dev):
+        if out is not None:
+            res = out
+            if tuple(res["P"].shape) != (S, 4, 4) or res["P"].device != dev or (return_all and "params" not in res):
+                raise ValueError("out buffers do not match this batch")
+            if return_all and tuple(res["params"].shape) != (S, I, 6):
+                raise ValueError("out buffers do not match this batch")
+        else:
+            res = dict(P=torch.empty((S, 4, 4), dtype=torch.float64, device=dev),
+                       cost=torch.empty((S,), dtype=torch.float64, device=dev),
+                       best=torch.empty((S,), dtype=torch.int32, device=dev),
+                       init_y_angle=torch.empty((S,), dtype=torch.float64, device=dev),
+                       n_pts=torch.empty((S,), dtype=torch.int32, device=dev),
+                       degenerate=torch.empty((S,), dtype=torch.int32, device=dev))
+            if return_all:
+                res.update(init=torch.empty((S, I, 4), dtype=torch.float64, device=dev),
+                           params=torch.empty((S, I, 6), dtype=torch.float64, device=dev),
+                           costs=torch.empty((S, I), dtype=torch.float64, device=dev),
+                           stats=torch.empty((S, I, 4), dtype=torch.int32, device=dev))
+        sp = _stream_ptr(stream)
+        ws = _workspace(lib.frustum_register_workspace_bytes(S, I, n_in), dev, sp)
+        rc = lib.frustum_register_batch_f32(
+            _ptr(xyz_in), _ptr(pred), n_in, Ns_in, S, I, int(seed), float(RY_SIGMA), float(T_AMPLITUDE), _ptr(K9),
+            lb.ctypes.data, ub.ctypes.data, float(H), float(W), int(max_iter), 1 if is_2d else 0, _ptr(res["P"]),
+            _ptr(res["cost"]), _ptr(res["best"]), _ptr(res["init_y_angle"]), _ptr(res["n_pts"]),
+            _ptr(res["degenerate"]), _ptr(res.get("init") if return_all else None),
+            _ptr(res.get("params") if return_all else None), _ptr(res.get("costs") if return_all else None),
+            _ptr(res.get("stats") if return_all else None), _ptr(ws), ws.numel(), sp)
+    _native.check(rc, "frustum_register_batch")
+    return res
 
 
 def solve_p_given_k(points, labels, K, init_y_angle, init_T, H, W, t_xyz_lower_bound, t_xyz_upper_bound,
@@ -287,10 +376,8 @@ def inside_mask_batch(xyz, n_pts, P, K, H, W, stream=None):
     """Batched get_inside_img_mask (registration_lsq.py:67-84): int8 [S,Ns], 1 inside / 0 outside / -1 padding."""
     _require_cuda()
     lib = _native.load()
-    S, _, Ns = xyz.shape
+    S, Ns = _check_cloud(xyz, None, n_pts, dtypes=(torch.float32,))
     dev = xyz.device
-    if xyz.dtype != torch.float32:
-        raise ValueError("inside_mask_batch takes float32 coordinates")
     P16 = torch.as_tensor(P, dtype=torch.float64).to(dev).reshape(S, -1)
     if P16.shape[1] == 12:
         P16 = torch.cat([P16, torch.tensor([[0.0, 0.0, 0.0, 1.0]], dtype=torch.float64, device=dev).expand(S, 4)], 1)

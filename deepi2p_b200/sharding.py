@@ -30,24 +30,43 @@ def unpack_records(rec):
     return rec[:, :16].reshape(-1, 4, 4), rec[:, 16]
 
 
-def gather_poses(P, cost, n_total=None, group=None):
-    """All-gather the per-rank results into global sample order.  Works for uneven shards (pads to
-    the largest shard).  Returns (P [S_total,4,4], cost [S_total]) on every rank."""
+def gather_poses(P, cost, n_total=None, group=None, out=None):
+    """All-gather the per-rank results into global sample order.  Returns (P [S_total,4,4], cost [S_total]) on every
+    rank.
+
+    Fast path (the benchmark's and any block partition's case): when `n_total` is given, every rank can work out all
+    shard sizes from partition() alone, so there is NO size exchange and no host synchronisation -- one
+    all_gather_into_tensor of the [S_local,17] f64 records (equal shards) or of records padded to the largest shard
+    (uneven ones).  Without `n_total` the shard sizes are exchanged first (one extra small collective + a host read).
+    `out`: optional preallocated [world * max_shard, 17] f64 buffer for the gathered records."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return P, cost
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
     rec = pack_records(P, cost)
-    n_local = torch.tensor([rec.shape[0]], dtype=torch.int64, device=rec.device)
-    counts = [torch.zeros_like(n_local) for _ in range(world)]
-    dist.all_gather(counts, n_local, group=group)
-    counts = [int(c.item()) for c in counts]
+    if n_total is not None:
+        counts = [partition(n_total, world, r) for r in range(world)]
+        counts = [b - a for a, b in counts]
+        if counts[rank] != rec.shape[0]:
+            raise RuntimeError("rank %d holds %d records, the block partition of %d gives it %d" % (
+                rank, rec.shape[0], n_total, counts[rank]))
+    else:
+        n_local = torch.tensor([rec.shape[0]], dtype=torch.int64, device=rec.device)
+        sizes = torch.empty((world,), dtype=torch.int64, device=rec.device)
+        dist.all_gather_into_tensor(sizes, n_local, group=group)
+        counts = [int(c) for c in sizes.tolist()]
     m = max(counts)
-    padded = torch.zeros((m, 17), dtype=torch.float64, device=rec.device)
-    padded[:rec.shape[0]] = rec
-    out = torch.empty((world * m, 17), dtype=torch.float64, device=rec.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
-    parts = [out[r * m:r * m + counts[r]] for r in range(world)]
-    full = torch.cat(parts, dim=0)
+    if rec.shape[0] != m:
+        padded = torch.zeros((m, 17), dtype=torch.float64, device=rec.device)
+        padded[:rec.shape[0]] = rec
+        rec = padded
+    if out is None or tuple(out.shape) != (world * m, 17) or out.device != rec.device:
+        out = torch.empty((world * m, 17), dtype=torch.float64, device=rec.device)
+    dist.all_gather_into_tensor(out, rec, group=group)
+    if min(counts) == m:
+        full = out
+    else:
+        full = torch.cat([out[r * m:r * m + counts[r]] for r in range(world)], dim=0)
     if n_total is not None and full.shape[0] != n_total:
         raise RuntimeError("gathered %d records, expected %d" % (full.shape[0], n_total))
     return unpack_records(full)

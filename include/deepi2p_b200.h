@@ -9,6 +9,7 @@
  *
  *   frustum_solve_batch_*   FrustumRegistration.solvePGivenK          evaluation/frustum_reg/src/registration.cpp:9-186,190-206
  *                           + the multi-start loop around it          evaluation/registration_lsq.py:127-186
+ *   frustum_register_batch_f32  the per-sample body of the driver     evaluation/registration_lsq.py:329-343
  *   frustum_residuals_*     the residual vector solvePGivenK returns  registration.cpp:150-155
  *   frustum_evaluate_*      (test hook: one cost/gradient/JtJ pass)   registration_{2d,3d}.hpp:34-68,105-127
  *   frustum_prepare_batch   get_initial_guess + init perturbation     evaluation/registration_lsq.py:196-220,163-164
@@ -42,6 +43,10 @@ int dib_abi_version(void);
 const char* dib_last_error(void);
 /* Number of SMs of the current device, or a negative error code. */
 int dib_device_sm_count(void);
+/* Measurement hook: two cudaEvent_t (created by the caller with timing enabled) that every following solve launch of
+ * the CALLING THREAD records on its stream right before and right after the solver kernel; (NULL, NULL) switches it
+ * off.  bench.py uses it to time the dominant kernel inside its timed steps. */
+void dib_profile_solve_events(void* start_event, void* stop_event);
 
 /* ------------------------------------------------------------------------------------------
  * Registration solver.
@@ -64,7 +69,9 @@ int dib_device_sm_count(void);
  *   stats_all  [S][I][4] int32 = (LM iterations, cloud passes (evaluations), line-search
  *                                 contractions, termination code)
  * Termination codes: 0 gradient tol, 1 parameter tol, 2 function tol, 3 max iterations,
- *   4 min trust-region radius, 5 too many invalid steps, 6 infeasible start (init returned).
+ *   4 min trust-region radius, 5 too many invalid steps, 6 infeasible start (init returned; its cost is the
+ *   cost evaluated at the init, as registration.cpp:150-155 does after the failed solve; 0 LM iterations, 0 passes
+ *   counted).
  * workspace: [dev] 256-byte aligned scratch of at least frustum_solve_workspace_bytes(S, I, n_stride) bytes:
  *   per-problem results, the per-group bounding-box table (1 B/point) and the packed {x,y,z,label} copy of the
  *   clouds (sized for the f64 record: 32 B/point) that the solver builds from the cloud at every call, i.e.
@@ -86,6 +93,22 @@ int frustum_solve_batch_f64(const double* xyz, const int8_t* label, const int32_
                             double* P16_out, double* cost_out, int32_t* best_out,
                             double* params_all, double* cost_all, int32_t* stats_all,
                             void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
+/* Same solve with a per-evaluation trace (parity tooling: tests/tools/trace_divergence.py compares it with the
+ * oracle's trace to find the first evaluation at which two trajectories part).
+ *   trace [S][I][trace_cap][16] f64 [dev], zero-filled by the call; record e of a problem is written when the
+ *   solver consumes its e-th cloud pass:  [0..5] evaluated point x_t (P entries), [6] cost at x_t, [7] cost of the
+ *   current iterate, [8] trust-region radius, [9] LM iteration, [10] phase (0 initial, 1 line-search sample,
+ *   2 candidate after a failed line search, 3 cost at an infeasible start), [11] 1 if x_t became the iterate,
+ *   [12] termination code after this evaluation (-1 = still running), [13] line-search step size, [14] model cost
+ *   change of the step, [15] 1 (record written).  Evaluations beyond trace_cap are not recorded. */
+int frustum_solve_traced_f32(const float* xyz, const int8_t* label, const int32_t* n_pts, int n_stride,
+                             const double* K9, const double* init, const double* lb3, const double* ub3,
+                             double H, double W, int max_iter, int is_2d, int S, int I,
+                             double* P16_out, double* cost_out, int32_t* best_out,
+                             double* params_all, double* cost_all, int32_t* stats_all,
+                             double* trace, int trace_cap,
+                             void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
 /* One evaluation pass per sample at explicit parameters x [S][6] f64:
  * cost_out [S], grad_out [S][6] (J^T r), JtJ_out [S][36] (row-major P x P in the top-left).
@@ -130,6 +153,22 @@ int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in,
                               int8_t* label_out,
                               int32_t* n_pts, double* init, double* init_y_angle, int32_t* degenerate,
                               void* workspace, size_t workspace_bytes, dib_stream_t stream);
+
+/* The whole per-sample body of evaluation/registration_lsq.py:329-343 in ONE call -- the batched entry point that
+ * replaces the reference's fork-per-solve loop (registration_lsq.py:142-186): frustum_prepare_batch_f32 (sort on) +
+ * frustum_solve_batch_f32 + arg-min + the degenerate-sample rule (no predicted-inside point: P = I, cost = 1e4,
+ * best = 0; :329-332).  Inputs as frustum_prepare_batch_f32 / frustum_solve_batch_f32.  Optional outputs (each may
+ * be NULL): init_y_angle_out [S] f64, n_pts_out [S] i32 (points kept by the front filter), degenerate_out [S] i32,
+ * init_out [S][I][4] f64, params_all / cost_all / stats_all as above.
+ * workspace: [dev] 256-byte aligned, >= frustum_register_workspace_bytes(S, I, n_in) (front-filtered clouds + the
+ * solver's workspace). */
+size_t frustum_register_workspace_bytes(int S, int I, int n_in);
+int frustum_register_batch_f32(const float* xyz_in, const int8_t* pred, int n_in, int n_in_stride, int S, int I,
+                               uint64_t seed, double ry_sigma, double t_amp, const double* K9, const double* lb3,
+                               const double* ub3, double H, double W, int max_iter, int is_2d, double* P16_out,
+                               double* cost_out, int32_t* best_out, double* init_y_angle_out, int32_t* n_pts_out,
+                               int32_t* degenerate_out, double* init_out, double* params_all, double* cost_all,
+                               int32_t* stats_all, void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Evaluation-side ops.

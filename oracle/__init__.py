@@ -42,11 +42,19 @@ def _prep_points(points):
     return pts
 
 
+EXT_EVAL = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
+                            ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                            ctypes.POINTER(ctypes.c_double))
+
+
 def solve(points, labels, K, init_y_angle, init_T, H, W, t_lb, t_ub, max_iter=500, is_2d=True,
-          want_residuals=True):
+          want_residuals=True, linear_solver=0, ext_eval=None, trace_cap=0):
     """Oracle for FrustumRegistration.solvePGivenK (registration.cpp:9-186).
 
-    Returns (P 4x4, final_cost, residuals, stats dict, params[6]).
+    Returns (P 4x4, final_cost, residuals, stats dict, params[6]) (+ trace [n,16] as a sixth element when
+    trace_cap > 0).  Parity-tooling options (defaults = the reference behaviour): linear_solver=1 solves the damped
+    normal equations by Cholesky (the CUDA kernel's arithmetic) instead of Householder QR; ext_eval(x6) -> (cost,
+    g[P], JtJ[P,P]) replaces the dual-number evaluation (needs linear_solver=1; residuals are then not returned).
     """
     lib = _lib("libfrustum_oracle.so")
     pts = _prep_points(points)
@@ -60,17 +68,38 @@ def solve(points, labels, K, init_y_angle, init_T, H, W, t_lb, t_ub, max_iter=50
     cost = ctypes.c_double(0.0)
     lib.frustum_oracle_num_residuals.restype = ctypes.c_int64
     rows = lib.frustum_oracle_num_residuals(_p(lab, ctypes.c_int32), ctypes.c_int64(n))
+    want_residuals = want_residuals and ext_eval is None
     res = np.zeros(rows) if want_residuals else None
     stats = np.zeros(8, dtype=np.int32)
     params = np.zeros(6)
-    lib.frustum_oracle_solve(
+    Pn = 4 if is_2d else 6
+    cb = None
+    if ext_eval is not None:
+        def _cb(_user, x6, c_out, g_out, A_out):
+            c, g, A = ext_eval(np.array([x6[j] for j in range(6)]))
+            c_out[0] = float(c)
+            for j in range(Pn):
+                g_out[j] = float(g[j])
+                for k in range(Pn):
+                    A_out[j * Pn + k] = float(A[j][k])
+            return 0
+        cb = EXT_EVAL(_cb)
+    trace = np.zeros((max(int(trace_cap), 1), 16)) if trace_cap > 0 else None
+    rc = lib.frustum_oracle_solve_ex(
         _p(pts, ctypes.c_double), _p(lab, ctypes.c_int32), ctypes.c_int64(n), _p(K9, ctypes.c_double),
         ctypes.c_double(float(init_y_angle)), _p(T, ctypes.c_double), ctypes.c_double(float(H)),
         ctypes.c_double(float(W)), _p(lb, ctypes.c_double), _p(ub, ctypes.c_double),
         ctypes.c_int(int(max_iter)), ctypes.c_int(1 if is_2d else 0), _p(P16, ctypes.c_double),
         ctypes.byref(cost), _p(res, ctypes.c_double) if want_residuals else None,
-        _p(stats, ctypes.c_int32), _p(params, ctypes.c_double))
-    return P16.reshape(4, 4), cost.value, res, dict(zip(STAT_FIELDS, stats.tolist())), params
+        _p(stats, ctypes.c_int32), _p(params, ctypes.c_double), ctypes.c_int(int(linear_solver)),
+        cb if cb is not None else ctypes.cast(None, EXT_EVAL), None,
+        _p(trace, ctypes.c_double) if trace is not None else None, ctypes.c_int(int(trace_cap)))
+    if rc != 0:
+        raise ValueError("frustum_oracle_solve_ex: ext_eval needs linear_solver=1")
+    out = (P16.reshape(4, 4), cost.value, res, dict(zip(STAT_FIELDS, stats.tolist())), params)
+    if trace is not None:
+        out = out + (trace[trace[:, 15] > 0],)
+    return out
 
 
 def evaluate(points, labels, K, x, H, W, is_2d=True):
@@ -149,7 +178,7 @@ def initial_guess(points, pred):
 
 
 def solve_multistart(points, labels, K, init_ry, init_t, H, W, t_lb, t_ub, max_iter=500, is_2d=True,
-                     threads=1):
+                     threads=1, linear_solver=0):
     """Multi-start driver (registration_lsq.py:142-186) over MATERIALISED inits
     init_ry [I], init_t [I,3].  Deterministic arg-min (lowest index wins ties; the reference's
     winner is racy).  Returns dict(P, cost, best, costs[I], params[I,6], stats[list])."""
@@ -159,7 +188,7 @@ def solve_multistart(points, labels, K, init_ry, init_t, H, W, t_lb, t_ub, max_i
 
     def one(i):
         return solve(points, labels, K, init_ry[i], init_t[i], H, W, t_lb, t_ub, max_iter, is_2d,
-                     want_residuals=False)
+                     want_residuals=False, linear_solver=linear_solver)
 
     if threads > 1:
         with ThreadPoolExecutor(threads) as ex:

@@ -18,6 +18,7 @@
 //     steps, default tolerances) from its documentation / memory of
 //     trust_region_minimizer.cc, levenberg_marquardt_strategy.cc, dense_qr_solver.cc,
 //     corrector.cc, loss_function.cc, line_search.cc, polynomial.cc, parameter_block.h.
+// Checked on the GPU box as well (profiles/r02_probe_ceres_gpu_box.txt): no Ceres, no Eigen there either.
 // Known deliberate deviation: roots of the degree-4 derivative polynomial in the 3-sample
 // line-search interpolation are found by Durand-Kerner iteration instead of companion
 // matrix eigenvalues (same roots, different rounding).
@@ -426,11 +427,83 @@ struct Stats {
 };
 
 // ---------------------------------------------------------------------------
+// Options of the parity tooling (all off = the reference behaviour restated above).
+//   linear_solver 1: solve the damped normal equations (Js^T Js + D^2) y = Js^T r by Cholesky, with the model cost
+//                    change from the same 4x4 / 6x6 quantities -- the arithmetic the CUDA kernel uses -- instead of
+//                    Householder QR on the (m + P) x P stacked matrix (DENSE_QR, what Ceres does).
+//   ext:             take cost, g = J^T r and J^T J of every evaluation from a callback (the CUDA evaluation kernel
+//                    through tests/tools/trace_divergence.py) instead of the dual-number pass above: the oracle's
+//                    CONTROL FLOW then runs on the kernel's sums, which separates control-logic differences from
+//                    summation-order differences.  Needs linear_solver 1 (no Jacobian rows are available).
+//   trace:           one 16-double record per evaluation, same layout as the kernel's frustum_solve_traced_f32.
+// ---------------------------------------------------------------------------
+typedef int (*ExternalEval)(void* user, const double* x6, double* cost, double* g6, double* JtJ36);
+struct Options {
+  int linear_solver = 0;
+  ExternalEval ext = nullptr;
+  void* ext_user = nullptr;
+  double* trace = nullptr;
+  int trace_cap = 0;
+};
+constexpr int kTraceRec = 16;
+
+// Buffers reused across the iterations of one solve (no heap traffic inside the loop).
+struct Workspace {
+  Eval ev, trial;
+  std::vector<double> Js, res, A, b;
+};
+
+// Cholesky solve of (As + diag(d2)) y = gs, As full symmetric P x P (the kernel's chol_solve, restated).
+bool chol_solve(int P, const double As[6][6], const double* d2, const double* gs, double* y) {
+  double L[6][6], inv[6], z[6];
+  bool ok = true;
+  for (int j = 0; j < P; ++j) {
+    double sacc = As[j][j] + d2[j];
+    for (int k = 0; k < j; ++k) sacc -= L[j][k] * L[j][k];
+    if (!(sacc > 0.0)) ok = false;
+    inv[j] = 1.0 / std::sqrt(sacc);
+    L[j][j] = sacc * inv[j];
+    for (int i = j + 1; i < P; ++i) {
+      double t = As[i][j];
+      for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+      L[i][j] = t * inv[j];
+    }
+  }
+  for (int i = 0; i < P; ++i) {
+    double t = gs[i];
+    for (int k = 0; k < i; ++k) t -= L[i][k] * z[k];
+    z[i] = t * inv[i];
+  }
+  for (int i = P - 1; i >= 0; --i) {
+    double t = z[i];
+    for (int k = i + 1; k < P; ++k) t -= L[k][i] * y[k];
+    y[i] = t * inv[i];
+  }
+  return ok;
+}
+
+// ---------------------------------------------------------------------------
 // The trust-region loop Ceres runs for the options at registration.cpp:137-147.
 // ---------------------------------------------------------------------------
-void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
+void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st, const Options& opt, Workspace& wsp) {
   const int P = pb.P;
   std::memset(st, 0, sizeof(*st));
+  const bool chol = opt.linear_solver == 1;
+  const bool ext = opt.ext != nullptr;
+  int n_rec = 0;
+  double* rec = nullptr;
+  auto trace_before = [&](const double* xt, double value, double x_cost, double radius, int iteration, int phase,
+                          double alpha, double mcc) {
+    rec = nullptr;
+    if (opt.trace == nullptr || n_rec >= opt.trace_cap) { ++n_rec; return; }
+    rec = opt.trace + (size_t)n_rec * kTraceRec;
+    ++n_rec;
+    for (int j = 0; j < 6; ++j) rec[j] = j < P ? xt[j] : 0.0;
+    rec[6] = value; rec[7] = x_cost; rec[8] = radius; rec[9] = (double)iteration; rec[10] = (double)phase;
+    rec[11] = 0.0; rec[12] = -1.0; rec[13] = alpha; rec[14] = mcc; rec[15] = 1.0;
+  };
+  auto trace_after = [&](int step_ok, int term) { if (rec) { rec[11] = (double)step_ok; rec[12] = (double)term; } };
+
   // Feasibility check (Program::IsFeasible) -- infeasible start => FAILURE, x untouched.
   for (int j = 0; j < P; ++j)
     if (x_user[j] < pb.lb[j] || x_user[j] > pb.ub[j]) { st->termination = 6; return; }
@@ -439,25 +512,50 @@ void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
   { double zero[6] = {0, 0, 0, 0, 0, 0}; plus_project(pb, x_user, zero, x); }
   double x_norm = 0.0; for (int j = 0; j < P; ++j) x_norm += x[j] * x[j]; x_norm = std::sqrt(x_norm);
 
-  Eval ev;
-  evaluate(pb, x, true, true, &ev);
+  // One evaluation at xx: cost, gradient and (QR mode) corrected residuals / Jacobian rows or (Cholesky mode) J^T J.
+  struct Sums { double cost, g[6], A[6][6]; };
+  auto eval_at = [&](const double* xx, Eval* ev, Sums* sm) {
+    if (ext) {
+      double x6[6] = {0, 0, 0, 0, 0, 0}, g6[6], JtJ[36];
+      for (int j = 0; j < P; ++j) x6[j] = xx[j];
+      opt.ext(opt.ext_user, x6, &sm->cost, g6, JtJ);
+      for (int j = 0; j < P; ++j) { sm->g[j] = g6[j]; for (int k = 0; k < P; ++k) sm->A[j][k] = JtJ[j * P + k]; }
+      return;
+    }
+    evaluate(pb, xx, true, true, ev);
+    sm->cost = ev->cost;
+    for (int j = 0; j < P; ++j) sm->g[j] = ev->g[j];
+    if (chol) {
+      for (int j = 0; j < P; ++j) for (int k = j; k < P; ++k) {
+        double acc = 0.0;
+        for (int64_t i = 0; i < pb.rows; ++i) acc += ev->J[i * P + j] * ev->J[i * P + k];
+        sm->A[j][k] = acc; sm->A[k][j] = acc;
+      }
+    }
+  };
+
+  Eval& ev = wsp.ev;
+  Sums cur;                                 // sums at the current iterate x
+  eval_at(x, &ev, &cur);
   st->jac_evals++; st->unique_evals++;
-  double x_cost = ev.cost;
-  std::vector<double> Js = ev.J;           // scaled in place below
-  std::vector<double> res = ev.r;
-  double g[6]; for (int j = 0; j < P; ++j) g[j] = ev.g[j];
+  double x_cost = cur.cost;
   const int64_t m = pb.rows;
+  std::vector<double>& Js = wsp.Js;          // scaled in place below (QR mode)
+  std::vector<double>& res = wsp.res;
+  if (!chol) { Js = ev.J; res = ev.r; }
+  double g[6]; for (int j = 0; j < P; ++j) g[j] = cur.g[j];
 
   // Jacobi scaling, computed once at iteration 0.
   for (int j = 0; j < P; ++j) {
     double s2 = 0.0;
-    for (int64_t i = 0; i < m; ++i) s2 += Js[i * P + j] * Js[i * P + j];
+    if (chol) s2 = cur.A[j][j];
+    else for (int64_t i = 0; i < m; ++i) s2 += Js[i * P + j] * Js[i * P + j];
     scale[j] = 1.0 / (1.0 + std::sqrt(s2));
   }
   auto scale_columns = [&](std::vector<double>& Jm) {
     for (int64_t i = 0; i < m; ++i) for (int j = 0; j < P; ++j) Jm[i * P + j] *= scale[j];
   };
-  scale_columns(Js);
+  if (!chol) scale_columns(Js);
   auto gradient_max_norm = [&](const double* xx, const double* gg) {
     double ng[6], proj[6], mx = 0.0;
     for (int j = 0; j < P; ++j) ng[j] = -gg[j];
@@ -475,6 +573,14 @@ void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
   double minimum_cost = x_cost;
   for (int j = 0; j < P; ++j) x_user[j] = x[j];
   st->successful_steps = 0;
+  trace_before(x, x_cost, 0.0, radius, 0, 0, 1.0, 0.0);
+  trace_after(1, -1);
+
+  std::vector<double>& A = wsp.A;
+  std::vector<double>& b = wsp.b;
+  if (!chol) { A.resize((m + P) * P); b.resize(m + P); }
+  Eval& trial = wsp.trial;           // evaluation at the current line-search sample
+  Sums tsum;
 
   for (;;) {
     // --- loop-top termination tests (FinalizeIterationAndCheckIfMinimizerCanContinue)
@@ -485,40 +591,63 @@ void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
     step_successful = false;
 
     // --- LM step: min || [Js; sqrt(diag/radius)] y - [r; 0] ||  (DENSE_QR), step = -y
-    if (!reuse_diag) {
-      for (int j = 0; j < P; ++j) {
-        double s2 = 0.0;
-        for (int64_t i = 0; i < m; ++i) s2 += Js[i * P + j] * Js[i * P + j];
-        diag[j] = std::min(std::max(s2, 1e-6), 1e32);
-      }
-    }
-    reuse_diag = true;
-    std::vector<double> A((m + P) * P, 0.0), b(m + P, 0.0);
-    std::memcpy(A.data(), Js.data(), sizeof(double) * m * P);
-    for (int j = 0; j < P; ++j) A[(m + j) * P + j] = std::sqrt(diag[j] / radius);
-    std::memcpy(b.data(), res.data(), sizeof(double) * m);
     double y[6];
-    bool ok = householder_lstsq(A, b, m + P, P, y);
-    for (int j = 0; j < P; ++j) { step[j] = -y[j]; if (!std::isfinite(step[j])) ok = false; }
+    bool ok;
     double mcc = 0.0;
-    if (ok) {
-      // model_cost_change = -(Js step)^T (r + Js step / 2)
-      for (int64_t i = 0; i < m; ++i) {
-        double mr = 0.0;
-        for (int j = 0; j < P; ++j) mr += Js[i * P + j] * step[j];
-        mcc -= mr * (res[i] + mr / 2.0);
+    if (chol) {
+      double As[6][6], gs[6], d2[6];
+      for (int j = 0; j < P; ++j) { gs[j] = g[j] * scale[j]; for (int k = 0; k < P; ++k) As[j][k] = cur.A[j][k] * scale[j] * scale[k]; }
+      if (!reuse_diag) for (int j = 0; j < P; ++j) diag[j] = std::min(std::max(As[j][j], 1e-6), 1e32);
+      reuse_diag = true;
+      const double inv_radius = 1.0 / radius;
+      for (int j = 0; j < P; ++j) d2[j] = diag[j] * inv_radius;
+      ok = chol_solve(P, As, d2, gs, y);
+      for (int j = 0; j < P; ++j) { step[j] = -y[j]; if (!std::isfinite(step[j])) ok = false; }
+      if (ok) {
+        double lin = 0.0, quad = 0.0;
+        for (int j = 0; j < P; ++j) {
+          lin += -y[j] * gs[j];
+          double rowsum = 0.0;
+          for (int k = 0; k < P; ++k) rowsum += As[j][k] * -y[k];
+          quad += -y[j] * rowsum;
+        }
+        mcc = -lin - 0.5 * quad;
+      }
+    } else {
+      if (!reuse_diag) {
+        for (int j = 0; j < P; ++j) {
+          double s2 = 0.0;
+          for (int64_t i = 0; i < m; ++i) s2 += Js[i * P + j] * Js[i * P + j];
+          diag[j] = std::min(std::max(s2, 1e-6), 1e32);
+        }
+      }
+      reuse_diag = true;
+      std::memcpy(A.data(), Js.data(), sizeof(double) * m * P);
+      std::memset(A.data() + m * P, 0, sizeof(double) * P * P);
+      for (int j = 0; j < P; ++j) A[(m + j) * P + j] = std::sqrt(diag[j] / radius);
+      std::memcpy(b.data(), res.data(), sizeof(double) * m);
+      std::memset(b.data() + m, 0, sizeof(double) * P);
+      ok = householder_lstsq(A, b, m + P, P, y);
+      for (int j = 0; j < P; ++j) { step[j] = -y[j]; if (!std::isfinite(step[j])) ok = false; }
+      if (ok) {
+        // model_cost_change = -(Js step)^T (r + Js step / 2)
+        for (int64_t i = 0; i < m; ++i) {
+          double mr = 0.0;
+          for (int j = 0; j < P; ++j) mr += Js[i * P + j] * step[j];
+          mcc -= mr * (res[i] + mr / 2.0);
+        }
       }
     }
     if (!ok || !(mcc > 0.0)) {
       if (++invalid >= 5) { st->termination = 5; break; }
-      radius *= 0.5; reuse_diag = true;
+      // LevenbergMarquardtStrategy::StepIsInvalid() == StepRejected(0): radius /= decrease_factor, factor doubles
+      radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
       continue;
     }
     invalid = 0;
     for (int j = 0; j < P; ++j) delta[j] = step[j] * scale[j];
 
     // --- projected Armijo line search along delta (bounds-constrained problems)
-    Eval trial;               // evaluation at the current line-search sample
     bool have_cand_eval = false;
     {
       double gd = 0.0, dmax = 0.0;
@@ -530,11 +659,12 @@ void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
         double sd[6], xt[6];
         for (int j = 0; j < P; ++j) sd[j] = alpha * delta[j];
         plus_project(pb, x, sd, xt);
-        evaluate(pb, xt, true, true, &trial);
+        eval_at(xt, &trial, &tsum);
         st->jac_evals++; st->unique_evals++;
-        s->x = alpha; s->value = trial.cost; s->value_valid = std::isfinite(trial.cost);
-        double gr = 0.0; for (int j = 0; j < P; ++j) gr += delta[j] * trial.g[j];
+        s->x = alpha; s->value = tsum.cost; s->value_valid = std::isfinite(tsum.cost);
+        double gr = 0.0; for (int j = 0; j < P; ++j) gr += delta[j] * tsum.g[j];
         s->gradient = gr; s->gradient_valid = s->value_valid && std::isfinite(gr);
+        trace_before(xt, tsum.cost, x_cost, radius, iteration, 1, alpha, mcc);
       };
       sample_at(1.0, &current);
       int ls_iter = 0; bool success = true;
@@ -555,13 +685,16 @@ void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
     // --- candidate point and its cost
     plus_project(pb, x, delta, cand);
     double cand_cost;
-    if (have_cand_eval) { cand_cost = trial.cost; st->cost_evals++; }
-    else { evaluate(pb, cand, true, true, &trial); cand_cost = trial.cost; st->cost_evals++; st->unique_evals++; }
+    if (have_cand_eval) { cand_cost = tsum.cost; st->cost_evals++; }
+    else {
+      eval_at(cand, &trial, &tsum); cand_cost = tsum.cost; st->cost_evals++; st->unique_evals++;
+      trace_before(cand, cand_cost, x_cost, radius, iteration, 2, 1.0, mcc);
+    }
 
     // --- parameter / function tolerance (x is NOT advanced when they fire)
     double sn = 0.0; for (int j = 0; j < P; ++j) sn += (x[j] - cand[j]) * (x[j] - cand[j]);
-    if (std::sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { st->termination = 1; break; }
-    if (std::fabs(x_cost - cand_cost) <= 1e-6 * x_cost) { st->termination = 2; break; }
+    if (std::sqrt(sn) <= 1e-8 * (x_norm + 1e-8)) { st->termination = 1; trace_after(0, 1); break; }
+    if (std::fabs(x_cost - cand_cost) <= 1e-6 * x_cost) { st->termination = 2; trace_after(0, 2); break; }
 
     const double rho = (x_cost - cand_cost) / mcc;
     if (rho > 1e-3) {
@@ -569,20 +702,28 @@ void minimize(const Problem& pb, double* x_user, int max_iter, Stats* st) {
       x_norm = 0.0; for (int j = 0; j < P; ++j) x_norm += x[j] * x[j]; x_norm = std::sqrt(x_norm);
       // Ceres re-evaluates residuals + Jacobian at the accepted point (same values).
       st->jac_evals++;
-      x_cost = trial.cost; Js = trial.J; res = trial.r;
-      for (int j = 0; j < P; ++j) g[j] = trial.g[j];
-      scale_columns(Js);
+      x_cost = tsum.cost;
+      cur = tsum;
+      if (!chol) { Js.swap(trial.J); res.swap(trial.r); scale_columns(Js); }
+      for (int j = 0; j < P; ++j) g[j] = tsum.g[j];
       grad_max = gradient_max_norm(x, g);
       radius = radius / std::max(1.0 / 3.0, 1.0 - std::pow(2.0 * rho - 1.0, 3));
       radius = std::min(1e16, radius);
       decrease_factor = 2.0; reuse_diag = false;
       step_successful = true; st->successful_steps++;
       if (x_cost < minimum_cost) { minimum_cost = x_cost; for (int j = 0; j < P; ++j) x_user[j] = x[j]; }
+      trace_after(1, -1);
     } else {
       radius = radius / decrease_factor; decrease_factor *= 2.0; reuse_diag = true;
+      trace_after(0, -1);
     }
   }
   st->iterations = iteration;
+  // the kernel's trace writes the termination code of loop-top exits into the last record
+  if (opt.trace && n_rec > 0 && n_rec <= opt.trace_cap) {
+    double* last = opt.trace + (size_t)(n_rec - 1) * kTraceRec;
+    if (last[12] < 0.0) last[12] = (double)st->termination;
+  }
 }
 
 // Pose matrix from the parameter vector (registration.cpp:161-185; AngleAxisToRotationMatrix).
@@ -634,26 +775,48 @@ int64_t frustum_oracle_num_residuals(const int32_t* labels, int64_t n) {
 
 // Restatement of solvePGivenK (registration.cpp:9-186).  pts = [x[N] | y[N] | z[N]] f64.
 // residuals may be NULL.  stats = 8 x int32 (struct Stats).  params_out = 6 doubles (final x).
-int frustum_oracle_solve(const double* pts, const int32_t* labels, int64_t n, const double* K9,
-                         double init_y_angle, const double* init_T, double H, double W,
-                         const double* lb3, const double* ub3, int max_iter, int is_2d,
-                         double* P16, double* final_cost, double* residuals, int32_t* stats,
-                         double* params_out) {
+// Parity-tooling extras (all 0 / NULL = the reference behaviour): linear_solver 1 = Cholesky on the normal equations;
+// ext / ext_user = external evaluation callback (needs linear_solver 1); trace [trace_cap][16] per-evaluation records.
+int frustum_oracle_solve_ex(const double* pts, const int32_t* labels, int64_t n, const double* K9,
+                            double init_y_angle, const double* init_T, double H, double W,
+                            const double* lb3, const double* ub3, int max_iter, int is_2d,
+                            double* P16, double* final_cost, double* residuals, int32_t* stats,
+                            double* params_out, int linear_solver, ExternalEval ext, void* ext_user,
+                            double* trace, int trace_cap) {
+  if (ext != nullptr && linear_solver != 1) return -1;
   Problem pb;
   setup_problem(&pb, pts, labels, n, K9, H, W, lb3, ub3, is_2d);
   double x[6] = {0, 0, 0, 0, 0, 0};
   if (is_2d) { x[0] = init_y_angle; for (int k = 0; k < 3; ++k) x[1 + k] = init_T[k]; }
   else { x[0] = 0; x[1] = init_y_angle; x[2] = 0; for (int k = 0; k < 3; ++k) x[3 + k] = init_T[k]; }
   Stats st;
-  minimize(pb, x, max_iter, &st);
-  Eval ev;
-  evaluate(pb, x, false, true, &ev);       // Problem::Evaluate, registration.cpp:150-155
-  *final_cost = ev.cost;
-  if (residuals) std::memcpy(residuals, ev.r.data(), sizeof(double) * pb.rows);
+  Options opt;
+  opt.linear_solver = linear_solver; opt.ext = ext; opt.ext_user = ext_user; opt.trace = trace; opt.trace_cap = trace_cap;
+  if (trace) std::memset(trace, 0, sizeof(double) * (size_t)trace_cap * kTraceRec);
+  Workspace wsp;
+  minimize(pb, x, max_iter, &st, opt, wsp);
+  if (ext) {
+    double g6[6], JtJ[36], x6[6] = {0, 0, 0, 0, 0, 0};
+    for (int j = 0; j < pb.P; ++j) x6[j] = x[j];
+    ext(ext_user, x6, final_cost, g6, JtJ);
+  } else {
+    evaluate(pb, x, false, residuals != nullptr, &wsp.ev);       // Problem::Evaluate, registration.cpp:150-155
+    *final_cost = wsp.ev.cost;
+    if (residuals) std::memcpy(residuals, wsp.ev.r.data(), sizeof(double) * pb.rows);
+  }
   pose_from_params(x, pb.P, P16);
   if (stats) std::memcpy(stats, &st, sizeof(st));
   if (params_out) for (int j = 0; j < 6; ++j) params_out[j] = (j < pb.P) ? x[j] : 0.0;
   return 0;
+}
+
+int frustum_oracle_solve(const double* pts, const int32_t* labels, int64_t n, const double* K9,
+                         double init_y_angle, const double* init_T, double H, double W,
+                         const double* lb3, const double* ub3, int max_iter, int is_2d,
+                         double* P16, double* final_cost, double* residuals, int32_t* stats,
+                         double* params_out) {
+  return frustum_oracle_solve_ex(pts, labels, n, K9, init_y_angle, init_T, H, W, lb3, ub3, max_iter, is_2d, P16,
+                                 final_cost, residuals, stats, params_out, 0, nullptr, nullptr, nullptr, 0);
 }
 
 // One evaluation at an explicit parameter vector: cost, g = J^T r (P), JtJ (P x P row-major),

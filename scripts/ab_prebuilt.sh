@@ -10,8 +10,8 @@ for item in "$@"; do
   python - "$item" <<'PY'
 import json, sys
 d = json.load(open("gpurun_out/sweep_tmp.json")); r = d["roofline"]
-print("%-24s reg/s %8.1f  kernel_ms %8.2f %s frac %.3f" % (sys.argv[1], d["value"], r["kernel_ms"], ["%.1f" % v for v in r.get("kernel_ms_all", [])], r["frac"]), flush=True)
+print("%-44s reg/s %8.1f  kernel_ms %8.2f %s frac %.3f tail_ms %s" % (sys.argv[1], d["value"], r["kernel_ms"], ["%.1f" % v for v in r.get("kernel_ms_all", [])], r["frac"], r.get("tail_ms")), flush=True)
 with open("gpurun_out/sweep.log", "a") as f:
-    f.write(json.dumps({"cfg": "prebuilt:" + sys.argv[1], "value": d["value"], "kernel_ms": r["kernel_ms"], "kernel_ms_all": r.get("kernel_ms_all"), "frac": r["frac"]}) + "\n")
+    f.write(json.dumps({"cfg": "prebuilt:" + sys.argv[1], "value": d["value"], "kernel_ms": r["kernel_ms"], "kernel_ms_all": r.get("kernel_ms_all"), "frac": r["frac"], "tail_ms": r.get("tail_ms")}) + "\n")
 PY
 done

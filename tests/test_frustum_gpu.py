@@ -163,6 +163,28 @@ def test_infeasible_start_returns_init(cuda):
     assert st["termination"] == 6
     er, et = pose_err(out["P"][0].cpu().numpy(), Po)
     assert er < 1e-12 and et < 1e-12
+    # the cost of an infeasible start is the cost AT the untouched init (registration.cpp:150-155 evaluates after the
+    # failed solve), not 0 -- a zero would win every arg-min over inits
+    assert co > 0 and abs(out["cost"][0].item() - co) <= 1e-10 * co
+    assert out["stats"][0, 0, 0].item() == 0 and out["stats"][0, 0, 1].item() == 0
+
+
+def test_mixed_feasible_and_infeasible_inits(cuda):
+    """One infeasible init among feasible ones must not win the arg-min with a fake zero cost."""
+    smp = small_sample(6)
+    xyz, lab, n_pts = frustum.pack_clouds(smp["points"], smp["pred"])
+    iy, _, _, _ = oracle.initial_guess(smp["points"], smp["pred"])
+    ry, t = syn.make_inits(6, iy, 3)
+    init = np.concatenate([ry[:, None], t], axis=1)
+    init = np.concatenate([np.array([[0.3, 0.0, 0.5, 1.0]]), init], axis=0)[None]      # init 0 infeasible (ty = 0.5)
+    out = frustum.solve_batch(xyz, lab, n_pts, smp["K"], init, smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500, True,
+                              return_all=True)
+    costs = out["costs"][0].cpu().numpy()
+    assert out["stats"][0, 0, 3].item() == 6 and costs[0] > 0
+    assert int(out["best"][0]) == int(np.argmin(costs))
+    ms = oracle.solve_multistart(smp["points"], smp["pred"], smp["K"], init[0, :, 0], init[0, :, 1:4], smp["H"],
+                                 smp["W"], syn.T_LB, syn.T_UB, 500, True)
+    assert abs(costs[0] - ms["costs"][0]) <= 1e-10 * ms["costs"][0]
 
 
 def test_ragged_empty_and_ignored_labels(cuda):

@@ -36,6 +36,16 @@ def _worker(rank, world, port, n_total):
     assert torch.equal(Pg[:, 0, 3], torch.arange(n_total, dtype=torch.float64))
     assert torch.equal(cg, torch.arange(n_total, dtype=torch.float64) * 10)
     assert torch.equal(Pg[:, 1, 1], torch.ones(n_total, dtype=torch.float64))
+    # without n_total the shard sizes are exchanged first; same result
+    Pg2, cg2 = sharding.gather_poses(P, cost)
+    assert torch.equal(Pg2, Pg) and torch.equal(cg2, cg)
+    # a shard that contradicts the block partition is an error, not a silent mis-gather
+    if n_total % world == 0:
+        try:
+            sharding.gather_poses(P[:-1], cost[:-1], n_total=n_total)
+            raise AssertionError("expected RuntimeError")
+        except RuntimeError:
+            pass
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Full-size parity study THROUGH THE PRODUCT PATH, with per-evaluation traces (run on the GPU box).
+
+    python tests/tools/trace_divergence.py --samples 24 --inits 60 --out profiles/r02_trace_divergence
+
+What it does (20480-point KITTI-shaped clouds, 1e-4 rad / 1e-3 m gate):
+
+  1. GPU: frustum.prepare_batch (initial guess, front filter, Morton SORT, device-made Philox inits) followed by the
+     traced solve -- exactly what register_batch runs (the one-call path is run too and must give the same bits).
+  2. CPU oracle (Ceres restatement, Householder QR) on the ORIGINAL unsorted cloud with the oracle's own
+     get_initial_guess filter and the device-made inits, also traced.
+  3. For EVERY solve outside the gate: the first evaluation at which the two traces part, the size of the difference
+     just before it (the rounding-level seed) and what kind of event it was (a decision that flipped -- Armijo,
+     step acceptance, a tolerance test -- or a smooth amplification across a kink of the objective).
+  4. The same comparison with the oracle switched to the kernel's linear algebra (normal equations + Cholesky), and
+     with the oracle's CONTROL FLOW run on the GPU kernel's own sums (external-evaluation hook): if the control logic
+     of the two implementations is the same, that hybrid must reproduce the GPU trajectory.
+
+Only tests/ may import oracle/ (test infrastructure); this file lives under tests/tools for that reason.
+"""
+import argparse
+import json
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+import oracle  # noqa: E402
+import torch  # noqa: E402
+from deepi2p_b200 import frustum, synthetic as syn  # noqa: E402
+
+ROT_TOL, TRANS_TOL = 1e-4, 1e-3
+PHASE = {0: "initial", 1: "line-search sample", 2: "candidate after failed line search", 3: "infeasible-start cost"}
+TERM = frustum.TERMINATION
+
+
+def param_diff(a, b, P):
+    nr = P - 3
+    return float(np.linalg.norm(a[:nr] - b[:nr])), float(np.linalg.norm(a[nr:P] - b[nr:P]))
+
+
+def first_divergence(tg, to, P):
+    """tg, to: [n,16] traces (valid records only).  Returns a dict describing where they part."""
+    n = min(len(tg), len(to))
+    scale = 1.0 + np.abs(to[:n, :P]).max(axis=1)
+    dx = np.abs(tg[:n, :P] - to[:n, :P]).max(axis=1) / scale
+    dv = np.abs(tg[:n, 6] - to[:n, 6]) / np.maximum(1e-300, np.abs(to[:n, 6]))
+    flags_equal = (tg[:n, 10] == to[:n, 10]) & (tg[:n, 11] == to[:n, 11]) & (tg[:n, 12] == to[:n, 12])
+    big = (dx > 1e-7) | ~flags_equal
+    if not big.any():
+        e = n                          # identical prefix; one side simply ran longer
+        kind = "one trace is a prefix of the other (different termination after %d common evaluations)" % n
+    else:
+        e = int(np.argmax(big))
+        if dx[e] <= 1e-7:              # same point, different verdict on it
+            what = []
+            if tg[e, 11] != to[e, 11]:
+                what.append("step acceptance (gpu %d, oracle %d)" % (tg[e, 11], to[e, 11]))
+            if tg[e, 12] != to[e, 12]:
+                tgc, toc = int(tg[e, 12]), int(to[e, 12])
+                what.append("termination test (gpu %s, oracle %s)" % (TERM[tgc] if tgc >= 0 else "continues",
+                                                                       TERM[toc] if toc >= 0 else "continues"))
+            if tg[e, 10] != to[e, 10]:
+                what.append("phase (gpu %s, oracle %s)" % (PHASE.get(int(tg[e, 10])), PHASE.get(int(to[e, 10]))))
+            kind = "decision flip on the same point: " + "; ".join(what)
+        elif e > 0 and tg[e, 10] != to[e, 10]:
+            kind = "line-search decision flip after evaluation %d (gpu next: %s, oracle next: %s)" % (
+                e - 1, PHASE.get(int(tg[e, 10])), PHASE.get(int(to[e, 10])))
+        elif e > 0 and tg[e, 9] == to[e, 9] and tg[e, 10] == 1 and abs(tg[e, 13] - to[e, 13]) > 1e-7 * abs(to[e, 13]):
+            kind = "line-search interpolation: same decisions, step size differs (gpu %.9g, oracle %.9g)" % (tg[e, 13], to[e, 13])
+        else:
+            kind = "smooth amplification (same decisions; the points drift apart across a kink of the objective)"
+    seed_idx = max(0, min(e, n) - 1)
+    lo = max(0, min(e, n) - 4)
+    return {
+        "first_divergent_evaluation": e, "common_evaluations": n, "evaluations_gpu": len(tg), "evaluations_oracle": len(to),
+        "kind": kind,
+        "seed_before": {"evaluation": seed_idx, "max_rel_dx": float(dx[seed_idx]) if n else None,
+                        "rel_dcost": float(dv[seed_idx]) if n else None},
+        "at_divergence": ({"max_rel_dx": float(dx[e]), "rel_dcost": float(dv[e]), "lm_iteration": int(tg[e, 9]),
+                           "phase_gpu": PHASE.get(int(tg[e, 10])), "phase_oracle": PHASE.get(int(to[e, 10]))}
+                          if e < n else None),
+        "rel_dx_profile": [float(v) for v in dx[lo:min(n, e + 3)]],
+    }
+
+
+def summarise(d_rot, d_tr):
+    d_rot, d_tr = np.asarray(d_rot), np.asarray(d_tr)
+    within = (d_rot < ROT_TOL) & (d_tr < TRANS_TOL)
+    q = lambda a: {"median": float(np.median(a)), "p90": float(np.percentile(a, 90)), "p99": float(np.percentile(a, 99)),
+                   "max": float(a.max())}
+    return {"solves": int(within.size), "within_gate": int(within.sum()), "fraction_within_gate": float(within.mean()),
+            "rot_rad": q(d_rot), "trans_m": q(d_tr)}, within
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples", type=int, default=24)
+    ap.add_argument("--inits", type=int, default=60)
+    ap.add_argument("--points", type=int, default=20480)
+    ap.add_argument("--first-id", type=int, default=1000)
+    ap.add_argument("--is-3d", action="store_true")
+    ap.add_argument("--cap", type=int, default=320)
+    ap.add_argument("--hybrid-in-gate", type=int, default=120, help="in-gate solves also replayed through the hybrid")
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "trace_divergence"))
+    args = ap.parse_args()
+    S, I, n, is_2d = args.samples, args.inits, args.points, not args.is_3d
+    P = 4 if is_2d else 6
+    dev = torch.device("cuda", 0)
+    threads = os.cpu_count() or 1
+
+    smps = [syn.make_sample(args.first_id + s, n) for s in range(S)]
+    Ns = (n + 15) // 16 * 16
+    xyz_h = np.zeros((S, 3, Ns), dtype=np.float32)
+    pred_h = np.full((S, Ns), -1, dtype=np.int8)
+    for s, smp in enumerate(smps):
+        xyz_h[s, :, :n] = smp["points"]
+        pred_h[s, :n] = smp["pred"]
+    xyz_in, pred_in = torch.from_numpy(xyz_h).to(dev), torch.from_numpy(pred_h).to(dev)
+    K, H, W = smps[0]["K"], smps[0]["H"], smps[0]["W"]
+    seed = 20260924
+
+    # ---- 1. the product path, traced
+    prep = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=seed)            # sort=True: what register_batch runs
+    g = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K, prep["init"], H, W, max_iter=500,
+                            is_2d=is_2d, return_all=True, trace_cap=args.cap)
+    reg = frustum.register_batch(xyz_in, pred_in, n, K, H, W, n_inits=I, seed=seed, max_iter=500, is_2d=is_2d,
+                                 return_all=True)
+    one_call_identical = bool(torch.equal(reg["params"], g["params"]) and torch.equal(reg["costs"], g["costs"])
+                              and torch.equal(reg["P"], g["P"]) and torch.equal(reg["init"], prep["init"]))
+    g_params = g["params"].cpu().numpy()
+    g_costs = g["costs"].cpu().numpy()
+    g_stats = g["stats"].cpu().numpy()
+    g_trace = g["trace"].cpu().numpy()
+    g_best = g["best"].cpu().numpy()
+    inits = prep["init"].cpu().numpy()
+    n_front = prep["n_pts"].cpu().numpy()
+
+    # ---- 2. the oracle on the original clouds with the device-made inits
+    per = []
+    for s, smp in enumerate(smps):
+        iy, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+        assert pf.shape[1] == int(n_front[s]), "front filter kept a different number of points"
+        assert abs(iy - float(prep["init_y_angle"][s])) < 1e-12
+        per.append((pf, lf))
+    jobs = [(s, i) for s in range(S) for i in range(I)]
+
+    def run_oracle(ls):
+        def one(job):
+            s, i = job
+            pf, lf = per[s]
+            return oracle.solve(pf, lf, K, inits[s, i, 0], inits[s, i, 1:4], H, W, syn.T_LB, syn.T_UB, 500, is_2d,
+                                want_residuals=False, linear_solver=ls, trace_cap=args.cap)
+        with ThreadPoolExecutor(threads) as ex:
+            return list(ex.map(one, jobs))
+
+    o_qr = run_oracle(0)
+    o_ch = run_oracle(1)
+
+    def compare(pa, pb):
+        dr, dt = zip(*[param_diff(pa[k], pb[k], P) for k in range(len(jobs))])
+        return summarise(dr, dt)
+
+    gp_flat = g_params.reshape(S * I, 6)
+    qr_p = np.stack([o[4] for o in o_qr])
+    ch_p = np.stack([o[4] for o in o_ch])
+    rep_gq, within_gq = compare(gp_flat, qr_p)
+    rep_gc, within_gc = compare(gp_flat, ch_p)
+    rep_qc, within_qc = compare(qr_p, ch_p)
+    same_counts = sum(int(g_stats[s, i, 0] == o_qr[s * I + i][3]["iterations"] and g_stats[s, i, 1] == o_qr[s * I + i][3]["unique_evals"]
+                          and g_stats[s, i, 3] == o_qr[s * I + i][3]["termination"]) for s, i in jobs)
+    rep_gq["identical_iteration_evaluation_termination"] = same_counts
+
+    # ---- registration level: best-of-I pose and cost
+    reg_ok = cost_le = 0
+    cost_rel = []
+    for s in range(S):
+        oc = np.array([o_qr[s * I + i][1] for i in range(I)])
+        bo, bg = int(np.argmin(oc)), int(g_best[s])
+        dr, dt = param_diff(g_params[s, bg], qr_p[s * I + bo], P)
+        reg_ok += int(dr < ROT_TOL and dt < TRANS_TOL)
+        cost_le += int(g_costs[s, bg] <= oc[bo] * (1 + 1e-9))
+        cost_rel.append(float(g_costs[s, bg] / oc[bo] - 1))
+
+    # ---- 3. first divergence of every out-of-gate solve (GPU vs oracle QR)
+    def valid(tr):
+        return tr[tr[:, 15] > 0]
+
+    out_of_gate = []
+    for k, (s, i) in enumerate(jobs):
+        if within_gq[k]:
+            continue
+        tg, to = valid(g_trace[s, i]), o_qr[k][5]
+        d = first_divergence(tg, to, P)
+        dr, dt = param_diff(gp_flat[k], qr_p[k], P)
+        d.update({"sample": args.first_id + s, "init": i, "final": {"rot_rad": dr, "trans_m": dt, "cost_gpu": float(g_costs[s, i]),
+                                                                     "cost_oracle": float(o_qr[k][1]),
+                                                                     "termination_gpu": TERM[int(g_stats[s, i, 3])],
+                                                                     "termination_oracle": TERM[o_qr[k][3]["termination"]]},
+                  "also_out_of_gate_oracle_qr_vs_oracle_cholesky": bool(not within_qc[k]),
+                  "in_gate_gpu_vs_oracle_cholesky": bool(within_gc[k])})
+        out_of_gate.append(d)
+
+    # ---- 4. hybrid: the oracle's control flow on the GPU kernel's sums (sorted cloud, same slices)
+    hybrid_jobs = [k for k in range(len(jobs)) if not within_gq[k]]
+    in_gate = [k for k in range(len(jobs)) if within_gq[k]]
+    hybrid_jobs += in_gate[:: max(1, len(in_gate) // max(1, args.hybrid_in_gate))][:args.hybrid_in_gate]
+    hyb = {"solves": 0, "bit_identical_final_params": 0, "within_gate": 0, "identical_trace_points": 0, "rows": []}
+    for k in hybrid_jobs:
+        s, i = jobs[k]
+        pf, lf = per[s]
+        xs, ls_, ns_ = prep["xyz"][s:s + 1], prep["label"][s:s + 1], prep["n_pts"][s:s + 1]
+
+        def ext(x6, xs=xs, ls_=ls_, ns_=ns_):
+            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d)
+            return float(c[0]), gr[0].cpu().numpy(), A[0].cpu().numpy()
+
+        o = oracle.solve(pf, lf, K, inits[s, i, 0], inits[s, i, 1:4], H, W, syn.T_LB, syn.T_UB, 500, is_2d,
+                         linear_solver=1, ext_eval=ext, trace_cap=args.cap)
+        dr, dt = param_diff(gp_flat[k], o[4], P)
+        tg, th = valid(g_trace[s, i]), o[5]
+        m = min(len(tg), len(th))
+        same_pts = bool(len(tg) == len(th) and np.array_equal(tg[:m, :P], th[:m, :P]))
+        hyb["solves"] += 1
+        hyb["bit_identical_final_params"] += int(np.array_equal(gp_flat[k][:P], o[4][:P]))
+        hyb["within_gate"] += int(dr < ROT_TOL and dt < TRANS_TOL)
+        hyb["identical_trace_points"] += int(same_pts)
+        if not (dr < ROT_TOL and dt < TRANS_TOL):
+            dd = first_divergence(tg, th, P)
+            dd.update({"sample": args.first_id + s, "init": i, "rot_rad": dr, "trans_m": dt})
+            hyb["rows"].append(dd)
+    hyb["of_which_out_of_gate_vs_oracle_qr"] = int(sum(1 for k in hybrid_jobs if not within_gq[k]))
+
+    kinds = {}
+    for d in out_of_gate:
+        key = d["kind"].split(":")[0].split("(")[0].strip()
+        kinds[key] = kinds.get(key, 0) + 1
+    seeds = [d["seed_before"]["max_rel_dx"] for d in out_of_gate if d["seed_before"]["max_rel_dx"] is not None]
+    report = {
+        "what": "GPU product path (prepare with Morton sort + device inits + solve; register_batch gives the same bits: %s) vs "
+                "CPU oracle on the original clouds; %d KITTI-shaped samples x %d inits, %d points, %s" % (
+                    one_call_identical, S, I, n, "4-DoF" if is_2d else "6-DoF"),
+        "gate": "1e-4 rad / 1e-3 m on the parameter vector of every solve",
+        "one_call_register_batch_bit_identical_to_prepare_plus_solve": one_call_identical,
+        "gpu_vs_oracle_qr": rep_gq,
+        "gpu_vs_oracle_cholesky": rep_gc,
+        "oracle_qr_vs_oracle_cholesky": rep_qc,
+        "registrations": {"count": S, "best_of_I_pose_within_gate": reg_ok, "gpu_best_cost_le_oracle_best_cost": cost_le,
+                          "best_cost_relative_difference": {"min": float(np.min(cost_rel)), "median": float(np.median(cost_rel)),
+                                                            "max": float(np.max(cost_rel))}},
+        "hybrid_oracle_control_on_gpu_sums_vs_gpu": hyb,
+        "out_of_gate_kinds": kinds,
+        "out_of_gate_seed_rel_dx": ({"min": float(np.min(seeds)), "median": float(np.median(seeds)), "max": float(np.max(seeds))}
+                                    if seeds else None),
+        "out_of_gate": out_of_gate,
+    }
+    os.makedirs(os.path.dirname(args.out), exist_ok=True)
+    with open(args.out + ".json", "w") as f:
+        json.dump(report, f, indent=1)
+    with open(args.out + ".md", "w") as f:
+        f.write("# Trace divergence report (%s)\n\n%s\n\n" % (os.path.basename(args.out), report["what"]))
+        f.write("| comparison | solves | within gate | fraction | median rot | max rot |\n|---|---|---|---|---|---|\n")
+        for name in ("gpu_vs_oracle_qr", "gpu_vs_oracle_cholesky", "oracle_qr_vs_oracle_cholesky"):
+            r = report[name]
+            f.write("| %s | %d | %d | %.4f | %.2e | %.2e |\n" % (name, r["solves"], r["within_gate"], r["fraction_within_gate"],
+                                                              r["rot_rad"]["median"], r["rot_rad"]["max"]))
+        f.write("\nidentical (iterations, evaluations, termination) GPU vs oracle: %d / %d\n" % (same_counts, len(jobs)))
+        f.write("\nregistrations: best-of-%d pose within gate %d / %d, GPU best cost <= oracle best cost %d / %d\n" % (
+            I, reg_ok, S, cost_le, S))
+        f.write("\nhybrid (oracle control flow on the GPU kernel's sums) vs GPU: %d solves (%d of them out of gate against the "
+                "QR oracle), bit-identical final parameters %d, identical evaluated points %d, within gate %d\n" % (
+                    hyb["solves"], hyb["of_which_out_of_gate_vs_oracle_qr"], hyb["bit_identical_final_params"],
+                    hyb["identical_trace_points"], hyb["within_gate"]))
+        f.write("\n## Every out-of-gate solve (GPU vs oracle QR): where the traces part\n\n")
+        f.write("| sample | init | first divergent eval | of (gpu/oracle) | seed rel dx before | rel dx at | kind | also QR-vs-Cholesky (CPU only) | final rot / trans |\n"
+                "|---|---|---|---|---|---|---|---|---|\n")
+        for d in out_of_gate:
+            at = d["at_divergence"]
+            f.write("| %d | %d | %d | %d/%d | %.1e | %s | %s | %s | %.1e / %.1e |\n" % (
+                d["sample"], d["init"], d["first_divergent_evaluation"], d["evaluations_gpu"], d["evaluations_oracle"],
+                d["seed_before"]["max_rel_dx"] or 0.0, ("%.1e" % at["max_rel_dx"]) if at else "-", d["kind"],
+                d["also_out_of_gate_oracle_qr_vs_oracle_cholesky"], d["final"]["rot_rad"], d["final"]["trans_m"]))
+    print(json.dumps({k: v for k, v in report.items() if k != "out_of_gate"}))
+
+
+if __name__ == "__main__":
+    main()
