@@ -42,10 +42,9 @@ def parse_args():
     ap.add_argument("--is-3d", action="store_true")
     ap.add_argument("--cpu-samples", type=int, default=3, help="registrations timed on the host cores")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=1,
-                    help="issue consecutive steps round-robin on this many CUDA streams (experimental: the tail of one "
-                         "step's persistent kernel then overlaps the head of the next step); 1 = serial steps with an "
-                         "L2 flush in between (the default the committed numbers use)")
+    ap.add_argument("--cpu-repeats", type=int, default=2, help="repetitions of the CPU sample (its run-to-run spread is reported)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE sub-config records (configs[0..2], 6-DoF)")
+    ap.add_argument("--config2-samples", type=int, default=4096)
     ap.add_argument("--ops", action="store_true", help="also time index_max / ball_query (config 3)")
     ap.add_argument("--ops-only", action="store_true", help="only time index_max / ball_query and print that JSON")
     return ap.parse_args()
@@ -259,6 +258,94 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def make_host_batch_threads(first_id, S, n_points, threads=16):
+    """make_host_batch over a thread pool (numpy releases the GIL in the heavy parts); used for the 4096-cloud config."""
+    from concurrent.futures import ThreadPoolExecutor
+    from deepi2p_b200 import synthetic as syn
+    Ns = (n_points + 15) // 16 * 16
+    xyz = np.zeros((S, 3, Ns), dtype=np.float32)
+    pred = np.full((S, Ns), -1, dtype=np.int8)
+
+    def one(s):
+        smp = syn.make_sample(first_id + s, n_points)
+        xyz[s, :, :n_points] = smp["points"]
+        pred[s, :n_points] = smp["pred"]
+
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(one, range(S)))
+    return xyz, pred
+
+
+class SolveTimer:
+    """CUDA events recorded by the library right before / after the solver kernel of every launch of this thread
+    (dib_profile_solve_events): the dominant kernel is timed INSIDE the timed steps, so kernel_ms <= ms_per_step."""
+
+    def __init__(self, torch, lib):
+        self.torch, self.lib = torch, lib
+        self.e0 = torch.cuda.Event(enable_timing=True)
+        self.e1 = torch.cuda.Event(enable_timing=True)
+        self.e0.record(); self.e1.record()                      # creates the underlying cudaEvent_t handles
+        torch.cuda.synchronize()
+
+    def __enter__(self):
+        self.lib.dib_profile_solve_events(self.e0.cuda_event, self.e1.cuda_event)
+        return self
+
+    def __exit__(self, *exc):
+        self.lib.dib_profile_solve_events(None, None)
+
+    def ms(self):
+        self.e1.synchronize()
+        return self.e0.elapsed_time(self.e1)
+
+
+def run_registration_config(torch, frustum, lib, dev, xyz_d, pred_d, n_points, K_d, H, W, n_inits, is_2d, steps, warmup,
+                            flush, peak, smi_index, seed0=1000):
+    """Device-resident timing of register_batch on one batch (used for the BASELINE sub-configs): per-step CUDA
+    events, solver-kernel events inside the steps, roofline fraction from the solver's own pass counters."""
+    S = xyz_d.shape[0]
+    sampler = ClockSampler(smi_index)
+    sampler.start()
+    outs = [None] * max(steps, 1)
+    for w in range(max(warmup, 1)):
+        outs[w % len(outs)] = frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=seed0 + w,
+                                                     max_iter=500, is_2d=is_2d, return_all=True, out=outs[w % len(outs)])
+    for k in range(len(outs)):
+        if outs[k] is None:
+            outs[k] = frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=seed0, max_iter=500,
+                                             is_2d=is_2d, return_all=True)
+    torch.cuda.synchronize()
+    step_ms, kern_ms, tails = [], [], []
+    sampler.mark_begin()
+    with SolveTimer(torch, lib) as st:
+        for k in range(steps):
+            flush()
+            torch.cuda.synchronize()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=seed0 + 100 + k, max_iter=500,
+                                   is_2d=is_2d, return_all=True, out=outs[k])
+            e1.record(); e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            kern_ms.append(st.ms())
+            tl = frustum.last_solve_timeline(dev, register_shape=(S, n_inits, n_points))
+            tails.append((tl[2] - tl[1]) * 1e-6)
+    sampler.mark_end()
+    clocks = sampler.stop()
+    pts_evals = 0.0
+    passes_mean = 0.0
+    for k in range(steps):
+        passes = outs[k]["stats"][:, :, 1].to(torch.float64)
+        pts_evals += float((passes * outs[k]["n_pts"].to(torch.float64)[:, None]).sum().item())
+        passes_mean += float(passes.mean().item()) / steps
+    ms = sum(step_ms) / steps
+    kms = sum(kern_ms) / steps
+    achieved = BYTES_PER_POINT * pts_evals / (sum(kern_ms) * 1e-3) / 1e9
+    return {"value": S / (ms * 1e-3), "unit": "registrations/s", "ms_per_step": ms, "kernel_ms": kms,
+            "tail_ms": sum(tails) / steps, "mean_cloud_passes_per_solve": passes_mean,
+            "achieved_GBps": achieved, "frac": achieved / peak, "steps": steps, "warmup": max(warmup, 1), "clocks": clocks}
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -281,23 +368,24 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group(backend="nccl", device_id=dev)
-    _native.load()
+    lib = _native.load()
+    peak, peak_src = load_measured_peaks()
 
     if args.ops_only:
-        print(json.dumps({"ops": bench_ops(torch, dev, load_measured_peaks()[0])}), flush=True)
+        print(json.dumps({"ops": bench_ops(torch, dev, peak)}), flush=True)
         return
     S_local, n_inits = workload_shape(args)
     is_2d = not args.is_3d
     n_points = args.points
-    xyz_h, pred_h, meta = make_host_batch(rank * S_local, S_local, n_points)
+    xyz_h, pred_h = make_host_batch_threads(rank * S_local, S_local, n_points)
+    meta = syn.make_sample(0, 16)
     Kmat, H, W = meta["K"], meta["H"], meta["W"]
     xyz_pin = torch.from_numpy(xyz_h).pin_memory()
     pred_pin = torch.from_numpy(pred_h).pin_memory()
     xyz_d = xyz_pin.to(dev)
     pred_d = pred_pin.to(dev)
     K_d = torch.as_tensor(Kmat, dtype=torch.float64).reshape(1, 9).expand(S_local, 9).contiguous().to(dev)
-    out_pin = torch.empty((S_local * world, 17), dtype=torch.float64).pin_memory()
-    out_pins = [out_pin] + [torch.empty_like(out_pin).pin_memory() for _ in range(max(args.streams, 1) - 1)]
+    n_total = S_local * world
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
     def flush_l2():
@@ -308,126 +396,128 @@ def main():
         if world > 1:
             dist.barrier()
 
-    seed_box = [0]
-
-    def step_resident():
-        seed_box[0] += 1
-        out = frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=seed_box[0],
-                                     max_iter=500, is_2d=is_2d)
-        P, c = sharding.gather_poses(out["P"], out["cost"])
-        return P, c
-
-    def step_e2e():
-        seed_box[0] += 1
-        x = xyz_pin.to(dev, non_blocking=True)
-        p = pred_pin.to(dev, non_blocking=True)
-        out = frustum.register_batch(x, p, n_points, K_d, H, W, n_inits=n_inits, seed=seed_box[0], max_iter=500,
-                                     is_2d=is_2d)
-        P, c = sharding.gather_poses(out["P"], out["cost"])
-        rec = sharding.pack_records(P, c)
-        if args.streams > 1:       # overlapped mode: one pinned result buffer per stream, the host does not wait here
-            out_pins[seed_box[0] % len(out_pins)][:rec.shape[0]].copy_(rec, non_blocking=True)
-        else:
-            out_pin[:rec.shape[0]].copy_(rec, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-        return rec.shape[0]
-
-    def timed(fn, steps):
-        total_ms = 0.0
-        for _ in range(steps):
-            flush_l2()
-            barrier()
-            e0 = torch.cuda.Event(enable_timing=True)
-            e1 = torch.cuda.Event(enable_timing=True)
-            e0.record()
-            fn()
-            e1.record()
-            e1.synchronize()
-            total_ms += e0.elapsed_time(e1)
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    streams = [torch.cuda.Stream(device=dev) for _ in range(max(args.streams, 1))] if args.streams > 1 else None
-
-    def timed_overlapped(fn, steps):
-        """K steps issued round-robin on the streams, ONE event pair around all of them (no flush in between:
-        every step streams 136 MB of input + a 168 MB packed copy, more than the 126 MB L2)."""
-        flush_l2()
-        barrier()
-        cur = torch.cuda.current_stream()
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for st in streams:
-            st.wait_stream(cur)
-        for k in range(steps):
-            with torch.cuda.stream(streams[k % len(streams)]):
-                fn()
-        for st in streams:
-            cur.wait_stream(st)
-        e1.record()
-        e1.synchronize()
-        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    if streams is not None:
-        timed = timed_overlapped                                       # noqa: F811 - experimental mode replaces the timer
-
-    # ---- warm-up (>= 3), then the timed region with clocks sampled during it
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     smi_index = vis.split(",")[local_rank].strip() if vis else str(local_rank)
+
+    # result buffers, one set per timed step (register_batch's out= reuse: no allocation inside the timed region)
+    n_bufs = max(args.steps, 2)
+    outs = [frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=1, max_iter=500, is_2d=is_2d,
+                                   return_all=True) for _ in range(n_bufs)]
+    gathered = [torch.empty((n_total, 17), dtype=torch.float64, device=dev) for _ in range(2)] if world > 1 else None
+    seed_box = [1]
+
+    def step_resident(k):
+        seed_box[0] += 1
+        out = frustum.register_batch(xyz_d, pred_d, n_points, K_d, H, W, n_inits=n_inits, seed=seed_box[0], max_iter=500,
+                                     is_2d=is_2d, return_all=True, out=outs[k % n_bufs])
+        if world > 1:
+            sharding.gather_poses(out["P"], out["cost"], n_total=n_total, out=gathered[k & 1])
+
+    # ---- warm-up (>= 3), then the timed region: per-step CUDA events, solver-kernel events inside each step
     sampler = ClockSampler(smi_index)
     if rank == 0:
         sampler.start()
-    for _ in range(max(args.warmup, 0)):
-        step_resident()
+    for w in range(max(args.warmup, 0)):
+        step_resident(w)
     barrier()
+    step_ms, kern_ms, tails = [], [], []
     sampler.mark_begin()
-    ms_total = timed(step_resident, args.steps)
+    with SolveTimer(torch, lib) as stimer:
+        for k in range(args.steps):
+            flush_l2()
+            barrier()
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_resident(k)
+            e1.record(); e1.synchronize()
+            step_ms.append(e0.elapsed_time(e1))
+            kern_ms.append(stimer.ms())
+            tl = frustum.last_solve_timeline(dev, register_shape=(S_local, n_inits, n_points))
+            tails.append((tl[2] - tl[1]) * 1e-6)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = S_local * world / (ms_per_step * 1e-3)
+    value = n_total / (ms_per_step * 1e-3)
+    k_ms = sum(kern_ms) / args.steps
+    # per-rank solver-kernel times: separates rank imbalance (slowest rank's kernel) from collective cost
+    kr = torch.tensor([k_ms], dtype=torch.float64, device=dev)
+    k_ranks = [kr.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(k_ranks, kr)
+    k_ranks = [float(x.item()) for x in k_ranks]
 
-    # ---- end to end through the public API with HOST buffers (H2D + D2H inside the timed region)
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps) / args.steps
-    e2e_value = S_local * world / (ms_e2e * 1e-3)
-    h2d = xyz_pin.numel() * 4 + pred_pin.numel()
-    d2h = S_local * world * 17 * 8
+    # ---- roofline of the dominant kernel from the timed steps themselves
+    pts_evals = 0.0
+    passes_mean = iters_mean = 0.0
+    for k in range(args.steps):
+        st_k = outs[k % n_bufs]["stats"].to(torch.float64)
+        passes = st_k[:, :, 1]
+        pts_evals += float((passes * outs[k % n_bufs]["n_pts"].to(torch.float64)[:, None]).sum().item())
+        passes_mean += float(passes.mean().item()) / args.steps
+        iters_mean += float(st_k[:, :, 0].mean().item()) / args.steps
+    alg_bytes = BYTES_PER_POINT * pts_evals / args.steps
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    compulsory = float(outs[0]["n_pts"].sum().item()) * BYTES_PER_POINT + S_local * (72 + 8 * 4 * n_inits + 136)
 
-    # ---- roofline of the dominant kernel: the solve launch alone, CUDA events on its stream
-    prep = frustum.prepare_batch(xyz_d, pred_d, n_points, n_inits, seed=12345)
-    res = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500,
-                              is_2d=is_2d, return_all=True)       # warm-up; its buffers are reused below (no allocation
-    k_ms = 0.0                                                     # inside the timed region)
-    k_all = []
-    reps = max(3, min(args.steps, 5))
-    for _ in range(reps):
+    # ---- end to end through the public API with HOST buffers.  Every step copies ITS inputs from pinned host memory
+    # and returns ITS result records to pinned host memory; copies run on a second stream into a second device buffer,
+    # so step k+1's host->device copy overlaps step k's solve (double buffering).  One event pair around the K steps.
+    copy_stream = torch.cuda.Stream(device=dev)
+    comp_stream = torch.cuda.Stream(device=dev)
+    x_bufs = [torch.empty_like(xyz_d) for _ in range(2)]
+    p_bufs = [torch.empty_like(pred_d) for _ in range(2)]
+    out_pins = [torch.empty((n_total, 17), dtype=torch.float64).pin_memory() for _ in range(2)]
+    pin_P = [torch.empty((n_total, 4, 4), dtype=torch.float64).pin_memory() for _ in range(2)]
+    pin_c = [torch.empty((n_total,), dtype=torch.float64).pin_memory() for _ in range(2)]
+
+    def run_e2e(steps):
+        copied = [None, None]
+        freed = [None, None]
+        for k in range(steps):
+            b = k & 1
+            with torch.cuda.stream(copy_stream):
+                if freed[b] is not None:
+                    copy_stream.wait_event(freed[b])          # the solve that last read this buffer is done
+                x_bufs[b].copy_(xyz_pin, non_blocking=True)
+                p_bufs[b].copy_(pred_pin, non_blocking=True)
+                copied[b] = torch.cuda.Event(); copied[b].record(copy_stream)
+            with torch.cuda.stream(comp_stream):
+                comp_stream.wait_event(copied[b])
+                seed_box[0] += 1
+                out = frustum.register_batch(x_bufs[b], p_bufs[b], n_points, K_d, H, W, n_inits=n_inits, seed=seed_box[0],
+                                             max_iter=500, is_2d=is_2d, return_all=True, out=outs[k % n_bufs])
+                freed[b] = torch.cuda.Event(); freed[b].record(comp_stream)
+                if world > 1:
+                    sharding.gather_poses(out["P"], out["cost"], n_total=n_total, out=gathered[b])
+                    out_pins[b].copy_(gathered[b], non_blocking=True)      # the gathered [S,17] records
+                else:
+                    pin_P[b].copy_(out["P"], non_blocking=True)           # two plain device->host copies, no kernel
+                    pin_c[b].copy_(out["cost"], non_blocking=True)
+
+    def timed_e2e(steps):
         flush_l2()
-        torch.cuda.synchronize()
+        barrier()
+        cur = torch.cuda.current_stream()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K_d, prep["init"], H, W, max_iter=500,
-                                  is_2d=is_2d, return_all=True, out=res)
+        copy_stream.wait_stream(cur); comp_stream.wait_stream(cur)
+        run_e2e(steps)
+        cur.wait_stream(copy_stream); cur.wait_stream(comp_stream)
         e1.record(); e1.synchronize()
-        k_all.append(e0.elapsed_time(e1))
-    k_ms = sum(k_all) / reps
-    tl = frustum.last_solve_timeline(dev)
-    tail_ms = (tl[2] - tl[1]) * 1e-6 if tl else None
-    span_ms = (tl[2] - tl[0]) * 1e-6 if tl else None
-    stats = res["stats"].to(torch.float64)
-    passes = stats[:, :, 1]
-    pts_evals = float((passes * prep["n_pts"].to(torch.float64)[:, None]).sum().item())
-    alg_bytes = BYTES_PER_POINT * pts_evals
-    peak, peak_src = load_measured_peaks()
-    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
-    compulsory = float(prep["n_pts"].sum().item()) * BYTES_PER_POINT + S_local * (72 + 8 * 4 * n_inits + 136)
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    timed_e2e(2)
+    ms_e2e = timed_e2e(args.steps) / args.steps
+    e2e_value = n_total / (ms_e2e * 1e-3)
+    h2d = xyz_pin.numel() * 4 + pred_pin.numel()
+    d2h = n_total * 17 * 8
 
     if rank != 0:
         if world > 1:
@@ -435,6 +525,7 @@ def main():
             dist.destroy_process_group()
         return
 
+    ncu = load_ncu_fractions(S_local, n_inits, is_2d)
     line = {
         "metric": "registrations/sec", "value": value, "unit": "registrations/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
@@ -444,83 +535,212 @@ def main():
                         "config 4" % (args.workload, S_local, n_points, n_inits, "4-DoF" if is_2d else "6-DoF"),
             "samples_per_gpu": S_local, "points": n_points, "inits": n_inits, "parallelism": "dp%d" % world,
             "why_this_workload": "the per-GPU shard of BASELINE configs[3] (4096 x 20480 x 60 over 8 GPUs), so that "
-                                 "N=1,2,4,8 time the same per-GPU work; configs[1] (4096 x 20480 x 1 init on one GPU) is "
-                                 "--workload single_init (profiles/r01_bench_final_single_init.json), configs[2] is --ops",
-            "l2": ("L2 flushed (256 MiB write) before every timed step; per-step CUDA events summed" if streams is None else
-                   "%d streams, steps overlapped, one event pair around all steps; inputs per step (136 MB + 168 MB packed "
-                   "copy) exceed the 126 MB L2, no flush in between" % len(streams)),
-            "step": "prepare (initial guess + front filter + Philox inits) + LM solve + arg-min"
-                    + (" + NCCL all-gather of [S,17] f64" if world > 1 else ""),
+                                 "N=1,2,4,8 time the same per-GPU work; configs[0], [1], [2] and the 6-DoF variant are the "
+                                 "`configs` sub-records of this line",
+            "l2": "value: L2 flushed (256 MiB write) before every timed step, per-step CUDA events summed; e2e: %d steps "
+                  "pipelined over two streams, one event pair, each step's inputs (136 MB) + packed copy (168 MB) exceed "
+                  "the 126 MB L2" % args.steps,
+            "step": "ONE C-ABI call frustum_register_batch_f32 = prepare (initial guess + front filter + Morton sort + "
+                    "Philox inits) + boxes + order + LM solve + arg-min/degenerate rule"
+                    + (" + one NCCL all_gather_into_tensor of [S,17] f64" if world > 1 else ""),
         },
         "e2e": {"value": e2e_value, "unit": "registrations/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "note": "pinned host xyz f32 + pred int8 -> device, register_batch, poses+cost -> pinned host"},
-        "gpu_launches": 5 * args.steps,   # prepare, boxes, order, solve, finalize per step
+                "d2h_bytes_per_step": d2h, "vs_resident": e2e_value / value,
+                "note": "per step: pinned host xyz f32 + pred int8 -> device buffer (copy stream, double-buffered), "
+                        "register_batch, [S,17] poses+cost -> pinned host; step k+1's copy overlaps step k's solve"},
+        "gpu_launches": 5 * args.steps,   # prepare, boxes, order, solve, finalize per step -- all this repo's kernels
         "clocks": clocks,
         "roofline": {
-            "bound": "hbm", "kernel": "frustum_solve_kernel<float,%d>" % (4 if is_2d else 6),
+            "bound": "issue",
+            "bound_note": "limiter per ncu = instruction issue / dependent fp64 latency (profiles/); DRAM moves ~1.3x the "
+                          "compulsory bytes. achieved/peak/frac below are SURVEY 8d's streamed-model HBM-equivalent: 13 B x "
+                          "points x cloud passes, divided by the measured copy bandwidth",
+            "kernel": "frustum_solve_kernel<float,%d>" % (4 if is_2d else 6),
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernel_ms_all": k_all,
-            "point_evals_per_s": pts_evals / (k_ms * 1e-3), "tail_ms": tail_ms, "kernel_span_ms": span_ms,
-            "mean_cloud_passes_per_solve": float(passes.mean().item()),
-            "mean_lm_iterations_per_solve": float(stats[:, :, 0].mean().item()),
+            "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": k_ms, "kernel_ms_all": kern_ms,
+            "kernel_ms_per_rank": {"min": min(k_ranks), "max": max(k_ranks), "all": k_ranks},
+            "kernel_timing": "CUDA events recorded by the library around the solver kernel inside each timed step "
+                             "(dib_profile_solve_events), rank 0; ms_per_step is the max over ranks",
+            "tail_ms": sum(tails) / len(tails),
+            "tail_note": "queue empty -> last CTA exit, from the kernel's own globaltimer words",
+            "point_evals_per_s": pts_evals / args.steps / (k_ms * 1e-3),
+            "mean_cloud_passes_per_solve": passes_mean, "mean_lm_iterations_per_solve": iters_mean,
             "compulsory_bytes_per_launch": compulsory,
             "traffic": load_traffic(S_local, n_inits, is_2d),
-            "ncu": load_ncu_fractions(S_local, n_inits, is_2d),
-            "note": "algorithmic = 13 B x points x cloud passes the solver performed (streamed model, SURVEY 8d); the "
-                    "cloud is re-read from L2/shared memory, so DRAM traffic (profiles/) is far below it",
+            "secondary": ncu,
         },
     }
 
-    # ---- CPU baseline + pose parity on a bounded sample (oracle port, all host cores)
-    if not args.no_cpu_baseline and world == 1 and args.cpu_samples > 0:
-        import oracle  # noqa: F401
-        cores = os.cpu_count() or 1
-        count = max(args.cpu_samples, cpu_batch_size(cores, n_inits))
-        cpu, dt = cpu_registrations(rank * S_local, count, n_points, n_inits, is_2d, cores)
-        worst_r = worst_t = 0.0
-        d_all, reg_ok, cost_le = [], 0, 0
-        Pn = 4 if is_2d else 6
-        for r in cpu:
-            xyz1, lab1, np1 = frustum.pack_clouds(r["pf"], r["lf"])
-            init = np.concatenate([r["ry"][:, None], r["t"]], axis=1)[None]
-            g = frustum.solve_batch(xyz1, lab1, np1, r["sample"]["K"], init, H, W, max_iter=500, is_2d=is_2d,
-                                    return_all=True)
-            Pg = g["P"][0].cpu().numpy()
-            c = (np.trace(Pg[:3, :3].T @ r["P"][:3, :3]) - 1.0) / 2.0
-            er = math.acos(max(-1.0, min(1.0, c)))
-            et = float(np.linalg.norm(Pg[:3, 3] - r["P"][:3, 3]))
-            worst_r, worst_t = max(worst_r, er), max(worst_t, et)
-            reg_ok += int(er < 1e-4 and et < 1e-3)
-            cost_le += int(float(g["cost"][0]) <= r["cost"] * (1 + 1e-9))
-            gp = g["params"][0].cpu().numpy()
-            nr = Pn - 3
-            d_rot = np.linalg.norm(gp[:, :nr] - r["params"][:, :nr], axis=1)
-            d_tr = np.linalg.norm(gp[:, nr:Pn] - r["params"][:, nr:Pn], axis=1)
-            d_all.append(np.stack([d_rot, d_tr], axis=1))
-        d_all = np.concatenate(d_all)
-        within = (d_all[:, 0] < 1e-4) & (d_all[:, 1] < 1e-3)
-        line["cpu_baseline"] = {
-            "value": count / dt, "unit": "registrations/s", "cores": cores, "kind": "port",
-            "sample": "%d registrations x %d inits of the same workload (first samples of the GPU batch), oracle port "
-                      "of the Ceres path, all solves spread over %d threads" % (count, n_inits, cores)}
-        line["parity"] = {
-            "gate": "1e-4 rad / 1e-3 m vs the CPU oracle (Ceres unavailable offline)",
-            "solves": int(within.size), "solves_within_gate": int(within.sum()),
-            "solve_median_rot_rad": float(np.median(d_all[:, 0])), "solve_median_trans_m": float(np.median(d_all[:, 1])),
-            "solve_max_rot_rad": float(d_all[:, 0].max()), "solve_max_trans_m": float(d_all[:, 1].max()),
-            "registrations": count, "registrations_within_gate": reg_ok,
-            "registrations_gpu_cost_le_oracle": cost_le,
-            "best_of_I_max_rot_err_rad": worst_r, "best_of_I_max_trans_err_m": worst_t,
-            "note": "trajectories are chaotic at rounding level: the CPU oracle against itself with an equivalent "
-                    "linear solver differs in ~3-4 % of solves (tests/tools/parity_sensitivity_cpu.py)"}
+    # ---- the other BASELINE configs, each a short device-resident run (world == 1 only: they are single-GPU configs)
+    if world == 1 and not args.no_configs:
+        cfgs = {}
+        try:
+            cfgs["single_sample_60_calls"] = bench_config1(torch, frustum, lib, dev, n_points, is_2d, flush_l2, peak, smi_index)
+        except Exception as e:  # noqa: BLE001
+            cfgs["single_sample_60_calls"] = {"error": repr(e)}
+        try:
+            S2 = args.config2_samples
+            x2, p2 = make_host_batch_threads(100000, S2, n_points)
+            x2d, p2d = torch.from_numpy(x2).to(dev), torch.from_numpy(p2).to(dev)
+            K2 = torch.as_tensor(Kmat, dtype=torch.float64).reshape(1, 9).expand(S2, 9).contiguous().to(dev)
+            r = run_registration_config(torch, frustum, lib, dev, x2d, p2d, n_points, K2, H, W, 1, True, 3, 3, flush_l2, peak,
+                                        smi_index)
+            r["workload"] = "BASELINE configs[1]: %d samples x %d pts x 1 init, 1 GPU" % (S2, n_points)
+            cfgs["single_init_4096"] = r
+            del x2d, p2d, x2, p2
+        except Exception as e:  # noqa: BLE001
+            cfgs["single_init_4096"] = {"error": repr(e)}
+        try:
+            S6 = min(256, S_local)
+            r = run_registration_config(torch, frustum, lib, dev, xyz_d[:S6].contiguous(), pred_d[:S6].contiguous(), n_points,
+                                        K_d[:S6].contiguous(), H, W, n_inits, False, 2, 2, flush_l2, peak, smi_index)
+            r["workload"] = "6-DoF (is_2d=False): %d samples x %d pts x %d inits" % (S6, n_points, n_inits)
+            cfgs["sixdof"] = r
+        except Exception as e:  # noqa: BLE001
+            cfgs["sixdof"] = {"error": repr(e)}
+        try:
+            cfgs["ops_config3"] = bench_ops(torch, dev, peak)
+        except Exception as e:  # noqa: BLE001
+            cfgs["ops_config3"] = {"error": repr(e)}
+        line["configs"] = cfgs
 
-    if args.ops:
+    # ---- CPU baseline + pose parity on a bounded sample (oracle port, all host cores), THROUGH the product path:
+    # the GPU side is register_batch (device initial guess, Morton sort, device-made inits); the oracle gets the original
+    # clouds, its own get_initial_guess filter and the same inits
+    if not args.no_cpu_baseline and world == 1 and args.cpu_samples > 0:
+        line.update(cpu_and_parity(torch, frustum, dev, args, xyz_d, pred_d, n_points, K_d, H, W, n_inits, is_2d))
+
+    if args.ops and "configs" not in line:
         line["ops"] = bench_ops(torch, dev, peak)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_config1(torch, frustum, lib, dev, n_points, is_2d, flush, peak, smi_index):
+    """BASELINE configs[0]: ONE sample, 60 inits.  (a) exactly as evaluation/registration_lsq.py:132-135 calls the
+    extension: 60 sequential FrustumRegistration.solvePGivenK calls with numpy float64 in / (P, cost, residuals) out,
+    arg-min on the host -- wall-clocked, because the call is host-synchronous by contract; (b) the batched replacement,
+    register_batch(S=1, I=60), device-timed."""
+    import importlib
+    from deepi2p_b200 import synthetic as syn
+    FR = importlib.import_module("deepi2p_b200.dropin.FrustumRegistration")
+    smp = syn.make_sample(424242, n_points)
+    pts64 = smp["points"].astype(np.float64)
+    # host-side get_initial_guess exactly as the reference caller does it (registration_lsq.py:196-220), numpy
+    inside = smp["pred"] == 1
+    mean = pts64[:, inside].mean(axis=1)
+    a = math.fmod(math.atan2(mean[2], mean[0]) - math.pi / 2 + math.pi, 2 * math.pi)
+    iy = (a + 2 * math.pi if a < 0 else a) - math.pi
+    c, s_ = math.cos(iy), math.sin(iy)
+    rz = -s_ * pts64[0] + c * pts64[2]
+    keep = rz > rz[inside].min() - 10
+    pf, lf = np.ascontiguousarray(pts64[:, keep]), smp["pred"][keep].astype(np.int64)
+    ry, t = syn.make_inits(424242, iy, 60)
+    lb, ub = list(syn.T_LB), list(syn.T_UB)
+    for i in range(3):                                                   # warm-up calls
+        FR.solvePGivenK(pf, lf, smp["K"], ry[i], t[i], smp["H"], smp["W"], lb, ub, 500, False, is_2d)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(smi_index)
+    sampler.start()
+    sampler.mark_begin()
+    reps, walls = 3, []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        best = None
+        for i in range(60):
+            P, cost, res = FR.solvePGivenK(pf, lf, smp["K"], ry[i], t[i], smp["H"], smp["W"], lb, ub, 500, False, is_2d)
+            if best is None or cost < best[1]:
+                best = (P, cost)
+        walls.append(time.perf_counter() - t0)
+    sampler.mark_end()
+    clocks = sampler.stop()
+    wall = min(walls)
+    # (b) the batched call on the same sample
+    Ns = (n_points + 15) // 16 * 16
+    xyz1 = np.zeros((1, 3, Ns), dtype=np.float32); xyz1[0, :, :n_points] = smp["points"]
+    pred1 = np.full((1, Ns), -1, dtype=np.int8); pred1[0, :n_points] = smp["pred"]
+    x1, p1 = torch.from_numpy(xyz1).to(dev), torch.from_numpy(pred1).to(dev)
+    K1 = torch.as_tensor(smp["K"], dtype=torch.float64).reshape(1, 9).to(dev)
+    rb = run_registration_config(torch, frustum, lib, dev, x1, p1, n_points, K1, smp["H"], smp["W"], 60, is_2d, 5, 3, flush,
+                                 peak, smi_index)
+    return {"workload": "BASELINE configs[0]: single sample, %d pts, 60 inits" % n_points,
+            "dropin_60_sequential_solvePGivenK": {"value": 1.0 / wall, "unit": "registrations/s", "ms_per_registration": wall * 1e3,
+                                                   "ms_per_call": wall * 1e3 / 60, "timing": "host wall clock, best of %d x 60 calls "
+                                                   "(numpy f64 in, numpy out, residual vector returned every call)" % reps,
+                                                   "all_ms": [w * 1e3 for w in walls], "clocks": clocks,
+                                                   "best_cost": float(best[1])},
+            "register_batch_S1_I60": rb}
+
+
+def cpu_and_parity(torch, frustum, dev, args, xyz_d, pred_d, n_points, K_d, H, W, n_inits, is_2d):
+    import oracle  # noqa: F401
+    from concurrent.futures import ThreadPoolExecutor
+    from deepi2p_b200 import synthetic as syn
+    cores = os.cpu_count() or 1
+    count = max(args.cpu_samples, cpu_batch_size(cores, n_inits))
+    seed = 777
+    g = frustum.register_batch(xyz_d[:count].contiguous(), pred_d[:count].contiguous(), n_points, K_d[:count].contiguous(), H, W,
+                               n_inits=n_inits, seed=seed, max_iter=500, is_2d=is_2d, return_all=True)
+    inits = g["init"].cpu().numpy()
+    gp = g["params"].cpu().numpy()
+    gc = g["costs"].cpu().numpy()
+    gbest = g["best"].cpu().numpy()
+    per, jobs = [], []
+    for c_ in range(count):
+        smp = syn.make_sample(c_, n_points)          # rank 0, first samples of the batch (seed = global sample id)
+        iy, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+        per.append((smp, pf, lf))
+        jobs += [(c_, i) for i in range(n_inits)]
+
+    def one(job):
+        c_, i = job
+        smp, pf, lf = per[c_]
+        return oracle.solve(pf, lf, smp["K"], inits[c_, i, 0], inits[c_, i, 1:4], smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500,
+                            is_2d, want_residuals=False)
+
+    dts, outs = [], None
+    for _ in range(max(1, args.cpu_repeats)):
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(max(1, cores)) as ex:
+            outs = list(ex.map(one, jobs))
+        dts.append(time.perf_counter() - t0)
+    dt = min(dts)
+    Pn = 4 if is_2d else 6
+    nr = Pn - 3
+    op = np.stack([o[4] for o in outs]).reshape(count, n_inits, 6)
+    oc = np.array([o[1] for o in outs]).reshape(count, n_inits)
+    d_rot = np.linalg.norm(gp[:, :, :nr] - op[:, :, :nr], axis=2).ravel()
+    d_tr = np.linalg.norm(gp[:, :, nr:Pn] - op[:, :, nr:Pn], axis=2).ravel()
+    within = (d_rot < 1e-4) & (d_tr < 1e-3)
+    reg_ok = cost_le = 0
+    worst_r = worst_t = 0.0
+    for c_ in range(count):
+        bo, bg = int(np.argmin(oc[c_])), int(gbest[c_])
+        er = float(np.linalg.norm(gp[c_, bg, :nr] - op[c_, bo, :nr])); et = float(np.linalg.norm(gp[c_, bg, nr:Pn] - op[c_, bo, nr:Pn]))
+        worst_r, worst_t = max(worst_r, er), max(worst_t, et)
+        reg_ok += int(er < 1e-4 and et < 1e-3)
+        cost_le += int(gc[c_, bg] <= oc[c_, bo] * (1 + 1e-9))
+    res = {"cpu_baseline": {
+        "value": count / dt, "unit": "registrations/s", "cores": cores, "kind": "port",
+        "sample": "%d registrations x %d inits of the same workload (first samples of the GPU batch, device-made inits), oracle "
+                  "port of the Ceres path (Ceres is installed neither here nor on the GPU box: profiles/r02_probe_ceres_gpu_box.txt), "
+                  "all solves spread over %d threads, best of %d runs" % (count, n_inits, cores, len(dts)),
+        "spread": {"runs_s": dts, "min_value": count / max(dts), "max_value": count / min(dts)}},
+        "parity": {
+        "gate": "1e-4 rad / 1e-3 m vs the CPU oracle (Ceres unavailable offline)",
+        "path": "GPU: register_batch (device initial guess + Morton sort + device-made inits); oracle: original clouds, own "
+                "get_initial_guess, same inits",
+        "solves": int(within.size), "solves_within_gate": int(within.sum()),
+        "solve_median_rot_rad": float(np.median(d_rot)), "solve_median_trans_m": float(np.median(d_tr)),
+        "solve_max_rot_rad": float(d_rot.max()), "solve_max_trans_m": float(d_tr.max()),
+        "registrations": count, "registrations_within_gate": reg_ok,
+        "registrations_gpu_cost_le_oracle": cost_le,
+        "best_of_I_max_rot_err_rad": worst_r, "best_of_I_max_trans_err_m": worst_t,
+        "note": "trajectories are chaotic at rounding level; every out-of-gate solve of a 1440-solve run is traced to its first "
+                "divergent evaluation in profiles/r02_trace_divergence.md"}}
+    return res
 
 
 def bench_ops(torch, dev, peak):

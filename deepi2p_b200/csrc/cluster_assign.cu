@@ -78,10 +78,14 @@ __global__ void __launch_bounds__(kCaThreads)
     for (int j = 0; j < K; ++j) o[j] = bi[j];
     const int m0 = bi[0];
     min_idx[(size_t)b * N + n] = m0;
-    atomicAdd(&s_cnt[m0], 1);
-    atomicAdd(&s_sum[m0], (unsigned long long)__double2ll_rn((double)x * kCaFixedScale));
-    atomicAdd(&s_sum[M + m0], (unsigned long long)__double2ll_rn((double)y * kCaFixedScale));
-    atomicAdd(&s_sum[2 * M + m0], (unsigned long long)__double2ll_rn((double)z * kCaFixedScale));
+    // a point with a non-finite coordinate has no fixed-point image: it keeps min_idx = 0 (every distance compares
+    // false) but is left out of its node's count and sums (the reference's float sum would turn the mean into NaN)
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      atomicAdd(&s_cnt[m0], 1);
+      atomicAdd(&s_sum[m0], (unsigned long long)__double2ll_rn((double)x * kCaFixedScale));
+      atomicAdd(&s_sum[M + m0], (unsigned long long)__double2ll_rn((double)y * kCaFixedScale));
+      atomicAdd(&s_sum[2 * M + m0], (unsigned long long)__double2ll_rn((double)z * kCaFixedScale));
+    }
   }
   __syncthreads();
   for (int i = tid; i < M; i += kCaThreads) {

@@ -627,7 +627,8 @@ struct ProbCtx {
   LMState<P> lm;
   const Entry<CT>* pk;                    // packed copy of the sample's cloud
   const float* box;                       // its box table
-  int rounds, slice_rounds, nslices;
+  int rounds, slice_rounds, nslices;      // of the OPEN pass (a young problem's pass is one slice, see open_pass)
+  int len_full, nslices_full;             // the cloud's fixed slicing, used from pass number slice_after on
   int prob;
   int next_slice;                         // claim counter of the open pass (>= nslices: nothing left to claim)
   int done;                               // slices of the open pass that are finished
@@ -656,11 +657,14 @@ __device__ __forceinline__ void box_load(const float* f, int slot, BoxRec& b) {
   for (int k = 0; k < 7; ++k) b.v[k] = __ldg(f + k * kRoundGroups + slot);
 }
 
-// Box test of one group by one lane: true if the group needs per-point work.
-__device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst& cc) {
+// Box test of one group by one lane.  0: every point of the group contributes exactly zero (skip); 1: undecided, the
+// points must be classified one by one; 2: every point of the (label-pure) group is surely active -- a "should be
+// outside" group that lies wholly inside the image or a "should be inside" group wholly outside it -- so its points go
+// straight to the exact path without the per-point fp32 classification.
+__device__ __forceinline__ int box_state(const BoxRec& b, const ClassConst& cc) {
   const int flags = __float_as_int(b.v[6]);
-  if (flags == 0) return false;                       // no point with a residual block
-  if (!cc.enabled) return true;
+  if (flags == 0) return 0;                           // no point with a residual block
+  if (!cc.enabled) return 1;
   const float cx = b.v[0], cy = b.v[1], cz = b.v[2], hx = b.v[3], hy = b.v[4], hz = b.v[5];
   const float m = 2.0f * fmaf(cc.G, (fabsf(cx) + hx) + (fabsf(cy) + hy) + (fabsf(cz) + hz), cc.G0);
   float lo[5], hi[5];
@@ -675,7 +679,9 @@ __device__ __forceinline__ bool box_undecided(const BoxRec& b, const ClassConst&
   const bool all_out = (hi[0] < -m) || (front && fminf(fminf(hi[1], -lo[2]), fminf(hi[3], -lo[4])) < -m);
   const bool all_in = front && fminf(fminf(lo[1], -hi[2]), fminf(lo[3], -hi[4])) > m;
   const bool skip = (!(flags & 1) || all_out) && (!(flags & 2) || all_in);
-  return !skip;
+  if (skip) return 0;
+  const bool sure = (flags == 1 && all_in) || (flags == 2 && all_out);
+  return sure ? 2 : 1;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -713,13 +719,15 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
   // so each exact evaluator has ONE code instance.
 #pragma unroll 1
   for (int r = r_begin; r <= r_end; ++r) {
-    unsigned mask = 0;
+    unsigned mask = 0, mask_sure = 0;       // undecided groups / groups whose points are all surely active
     int threshold = 1;
     if (r < r_end) {
       threshold = kBatch;
       box_cur = box_nxt;                              // loaded while the previous round was processed
       if (r + 1 < r_end) box_load(box_s + (size_t)(r + 1) * kBoxRoundFloats, lane, box_nxt);
-      mask = __ballot_sync(0xffffffffu, box_undecided(box_cur, cc));
+      const int bs = box_state(box_cur, cc);
+      mask = __ballot_sync(0xffffffffu, bs == 1);
+      mask_sure = __ballot_sync(0xffffffffu, bs == 2);
     }
     // Undecided groups are taken DIB_GPS at a time.  Their loads are issued first, then the pending
     // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
@@ -728,14 +736,18 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
     do {
       CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
       int glab[DIB_GPS];
-      const bool have = mask != 0;
+      // surely-active groups first (a step made only of them skips the classification), then the undecided ones
+      const bool have = (mask | mask_sure) != 0;
+      bool all_sure = true;
       if (have) {
 #pragma unroll
         for (int u = 0; u < DIB_GPS; ++u) {
           glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
-          if (mask) {
-            const int b = __ffs(mask) - 1;
-            mask &= mask - 1;
+          if (mask | mask_sure) {
+            const bool from_sure = mask_sure != 0;
+            const int b = __ffs(from_sure ? mask_sure : mask) - 1;
+            if (from_sure) mask_sure &= mask_sure - 1; else mask &= mask - 1;
+            all_sure = all_sure && from_sure;
             const Entry<CT> e = pk_s[(size_t)(r * kRoundGroups + b) * 32 + lane];      // this lane's point
             glab[u] = (int)e.lab; gx[u] = e.x; gy[u] = e.y; gz[u] = e.z;
           }
@@ -769,8 +781,13 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
       }
       if (have) {
         bool mb[DIB_GPS];
+        if (all_sure) {                                  // warp-uniform: only padding / ignored labels drop out
 #pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
+          for (int u = 0; u < DIB_GPS; ++u) mb[u] = (unsigned)glab[u] <= 1u;
+        } else {
+#pragma unroll
+          for (int u = 0; u < DIB_GPS; ++u) mb[u] = maybe_active<P>((float)gx[u], (float)gy[u], (float)gz[u], glab[u], cc);
+        }
 #pragma unroll
         for (int u = 0; u < DIB_GPS; ++u) {
           const unsigned m1 = __ballot_sync(0xffffffffu, mb[u] && glab[u] == 1);
@@ -788,7 +805,7 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
           pend1 += __popc(m1);
         }
       }
-    } while (mask);
+    } while (mask | mask_sure);
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
@@ -1287,6 +1304,7 @@ struct SolveArgs {
   const int32_t* perm;  // [S][I] inits of each sample, longest-predicted first
   int chunk;            // samples per scheduling chunk
   int slice_rounds;     // rounds per slice (before the kMaxSlices stretch)
+  int slice_after;      // passes of a problem that run as ONE slice before the fixed slicing starts
   double* trace;        // optional [S*I][trace_cap][kTraceRec] per-evaluation records, or NULL
   int trace_cap;
 };
@@ -1329,8 +1347,15 @@ __device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *rei
 __device__ __forceinline__ void st_volatile(int* p, int v) { *reinterpret_cast<volatile int*>(p) = v; }
 
 // Lane 0 of the owner: publish the pass whose pose / classification constants were just written.
+// A pass is cut into slices only from the problem's slice_after-th pass on: short solves (most of them) never pay the
+// per-slice overhead (rings drained and accumulators reduced at every slice end), while the long solves that make up
+// the end-of-kernel tail can be helped.  The switch depends on the problem's own pass count only, so results stay
+// independent of the batch, of the schedule and of who helps.
 template <typename CT, int P>
-__device__ __forceinline__ void open_pass(Smem<CT, P>& sm, ProbCtx<CT, P>& me, int warp) {
+__device__ __forceinline__ void open_pass(Smem<CT, P>& sm, ProbCtx<CT, P>& me, int warp, int slice_after) {
+  const bool sliced = me.lm.evals >= slice_after;
+  me.nslices = sliced ? me.nslices_full : 1;
+  me.slice_rounds = sliced ? me.len_full : (me.rounds > 0 ? me.rounds : 1);
   st_volatile(&me.done, 0);
   __threadfence_block();                       // pose, cls, done before the pass becomes claimable
   atomicOr(&sm.open_mask, 1u << warp);         // bit first: whoever claims the last slice clears it again
@@ -1413,12 +1438,12 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         me.pk = reinterpret_cast<const Entry<CT>*>(a.packed) + (size_t)s * a.rounds_max * kRoundPoints;
         me.box = a.boxes + (size_t)s * a.rounds_max * kBoxRoundFloats;
         me.rounds = rounds;
-        me.slice_rounds = len;
-        me.nslices = rounds > 0 ? (rounds + len - 1) / len : 1;    // an empty cloud still has one (empty) slice
+        me.len_full = len;
+        me.nslices_full = rounds > 0 ? (rounds + len - 1) / len : 1;    // an empty cloud still has one (empty) slice
         make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &me.cam);
         rc = lm_begin<P>(me.lm, a.init + (size_t)prob * 4, a.lb, a.ub, a.max_iter);
         n_rec = 0;
-        if (rc == LM_EVAL) { make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls); open_pass<CT, P>(sm, me, warp); }
+        if (rc == LM_EVAL) { make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls); open_pass<CT, P>(sm, me, warp, a.slice_after); }
       }
       __syncwarp();                                     // lane 0's problem set-up is visible to the whole warp
       rc = __shfl_sync(0xffffffffu, rc, 0);
@@ -1463,7 +1488,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
           ++n_rec;
           if (rc == LM_EVAL) {
             make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls);
-            open_pass<CT, P>(sm, me, warp);
+            open_pass<CT, P>(sm, me, warp, a.slice_after);
           } else {
             const LMState<P>& st = me.lm;
             double* po = a.params_all + (size_t)me.prob * 6;
@@ -1596,7 +1621,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) frustum_evaluate_kernel(const
                                                                            const double* K9, const double* x, double H,
                                                                            double W, const float* boxes,
                                                                            const Entry<CT>* packed, int rounds_max,
-                                                                           int slice_rounds, double* cost_out,
+                                                                           int slice_rounds, int sliced, double* cost_out,
                                                                            double* grad_out, double* JtJ_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   EvalSmem<CT, P>& sm = *reinterpret_cast<EvalSmem<CT, P>*>(smem_raw);
@@ -1607,7 +1632,7 @@ __global__ void __launch_bounds__(kEvalWarps * 32) frustum_evaluate_kernel(const
   if (tid == 0) {
     const int n = n_pts ? n_pts[s] : n_stride;
     const int rounds = box_rounds(n);
-    const int len = slice_len(rounds, slice_rounds);
+    const int len = sliced ? slice_len(rounds, slice_rounds) : (rounds > 0 ? rounds : 1);
     pb.pk = packed + (size_t)s * rounds_max * kRoundPoints;
     pb.box = boxes + (size_t)s * rounds_max * kBoxRoundFloats;
     pb.rounds = rounds;
@@ -1676,6 +1701,18 @@ static size_t packed_bytes(int S, int n_stride) {
   return align_up((size_t)(S > 0 ? S : 0) * box_rounds(n_stride) * kRoundPoints * sizeof(Entry<double>), 256);
 }
 
+#ifndef DIB_SLICE_AFTER
+#define DIB_SLICE_AFTER 48
+#endif
+static int default_slice_after() {
+  static const int v = [] {
+    const char* e = getenv("DIB_SLICE_AFTER");           // tuning knob; results depend on it at rounding level only
+    const int x = e ? atoi(e) : DIB_SLICE_AFTER;
+    return x < 0 ? 0 : x;
+  }();
+  return v;
+}
+
 static int default_slice_rounds() {
   static const int v = [] {
     const char* e = getenv("DIB_SLICE_ROUNDS");          // tuning knob; results depend on it at rounding level only
@@ -1709,6 +1746,7 @@ static int check_cloud_args(const CT* xyz, const int8_t* label, int n_stride, in
 
 // Optional CUDA events recorded right before / after the solve kernel on its launch stream (dib_profile_solve_events):
 // lets a benchmark time the dominant kernel INSIDE its timed steps instead of in a separate loop.
+static thread_local int g_eval_pass = 0;        // dib_evaluate_pass_index: which pass of a solve frustum_evaluate_* mimics
 static thread_local void* g_ev_start = nullptr;
 static thread_local void* g_ev_stop = nullptr;
 
@@ -1746,12 +1784,14 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   // one problem per CTA first (the kernel deals the first wave rank-major), so the spare warps of every CTA help.
   long long grid = (long long)cfg.sms * cfg.per_sm;
   if (grid > total) grid = total;
-  // scheduling chunk: as many samples as keep the concurrently touched clouds around 32 MB (a quarter of
-  // L2), and at least ~2x the resident problems.  Measured on B200 (512 x 60 problems, round 1): 1 or 50 samples
-  // 103.3 ms, 128 samples 97.7 ms, 256 samples 99.8 ms, 512 samples (no chunking) ~100 ms.
+  // scheduling chunk: the queue walks chunks of samples rank-major (longest-predicted inits of every sample of the
+  // chunk first).  Larger chunks start the long solves earlier (shorter tail); smaller chunks keep the packed clouds
+  // of the concurrently running problems inside the 126 MB L2.  Measured on B200, 512 x 60 problems, this kernel
+  // (profiles/r02_sweep_schedule.jsonl): 64 samples 90.5 ms, 98 (32 MB) 90.4, 128 89.5, 171 88.8, 256 (84 MB) 87.2,
+  // 512 (no chunking, 167 MB) 88.7 -> aim at ~80 MB of packed clouds per chunk, at least ~2x the resident problems.
   long long chunk = (2 * grid * kW + a.I - 1) / a.I;
   const long long bytes_per_sample = (long long)a.rounds_max * kRoundPoints * (long long)sizeof(Entry<CT>);
-  if (bytes_per_sample > 0 && chunk < (32ll << 20) / bytes_per_sample) chunk = (32ll << 20) / bytes_per_sample;
+  if (bytes_per_sample > 0 && chunk < (80ll << 20) / bytes_per_sample) chunk = (80ll << 20) / bytes_per_sample;
   if (const char* e = getenv("DIB_CHUNK_SAMPLES")) chunk = atoll(e);   // tuning knob
   if (chunk < 1) chunk = 1;
   if (chunk > a.S) chunk = a.S;
@@ -1819,6 +1859,7 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   a.H = H; a.W = W; a.max_iter = max_iter; a.S = S; a.I = I;
   a.chunk = 1;
   a.slice_rounds = default_slice_rounds();
+  a.slice_after = default_slice_after();
   a.trace = trace; a.trace_cap = trace_cap;
   DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
   DIB_CHECK_CUDA(cudaMemsetAsync((unsigned char*)a.queue + 8, 0xff, 16, st));   // timeline minima start at ~0ull
@@ -1853,7 +1894,8 @@ static int launch_evaluate(const int32_t* n_pts, int n_stride, const double* K9,
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   kern<<<S, kEvalWarps * 32, smem, st>>>(n_pts, n_stride, K9, x, H, W, table, packed, box_rounds(n_stride),
-                                         default_slice_rounds(), cost_out, grad_out, JtJ_out);
+                                         default_slice_rounds(), g_eval_pass >= default_slice_after() ? 1 : 0, cost_out,
+                                         grad_out, JtJ_out);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }
@@ -1903,6 +1945,8 @@ extern "C" {
 
 int dib_abi_version(void) { return 3; }
 const char* dib_last_error(void) { return dib::g_err; }
+
+void dib_evaluate_pass_index(int pass_index) { dib::g_eval_pass = pass_index < 0 ? 0 : pass_index; }
 
 void dib_profile_solve_events(void* start_event, void* stop_event) {
   dib::g_ev_start = start_event;

@@ -212,10 +212,12 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
     return res
 
 
-def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None):
-    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook)."""
+def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None, pass_index=0):
+    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook).  pass_index: reproduce the sums of
+    that pass of a solve bit for bit (the solver cuts a pass into slices from its DIB_SLICE_AFTER-th pass on)."""
     _require_cuda()
     lib = _native.load()
+    lib.dib_evaluate_pass_index(int(pass_index))
     S, Ns = _check_cloud(xyz, label, n_pts)
     dev = xyz.device
     K9 = _as_K(K, S, dev)

@@ -63,7 +63,10 @@ _xyz_ws = {}
 def ball_query_xyz_forward(points, nodes, radius, K):
     """Grid-hash radius search from coordinates: points [B,3,N], nodes [B,3,M] float32 CUDA -> int32 [B,M,K]
     with the ball_query contract (first K indices in ascending n within radius; none -> 0; fewer -> cyclic).
-    Equivalent to ball_query_forward on the float32 distance matrix, without ever building it."""
+    The contract is on SQUARED float32 distances: hit <=> ((dx*dx + dy*dy) + dz*dz) <= radius*radius (no fma), which
+    is what ball_query_forward gives on a matrix of those squared distances with radius^2.  The reference pipeline
+    thresholds torch.norm (the rounded square root) against radius; the two can differ for a distance within one
+    float32 ulp of the radius.  Points with a NaN coordinate never hit."""
     _check_input(points, "points", torch.float32)
     _check_input(nodes, "nodes", torch.float32)
     if points.dim() != 3 or nodes.dim() != 3 or points.shape[1] != 3 or nodes.shape[1] != 3 or points.shape[0] != nodes.shape[0]:

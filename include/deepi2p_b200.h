@@ -110,6 +110,11 @@ int frustum_solve_traced_f32(const float* xyz, const int8_t* label, const int32_
                              double* trace, int trace_cap,
                              void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
+/* frustum_evaluate_* reproduces, bit for bit, the sums the solver forms at pass number `pass_index` of a solve (the
+ * solver evaluates a problem's first DIB_SLICE_AFTER passes as one slice and later ones as a fixed sequence of
+ * slices; the two differ at rounding level).  Thread-local, default 0.  Parity tooling. */
+void dib_evaluate_pass_index(int pass_index);
+
 /* One evaluation pass per sample at explicit parameters x [S][6] f64:
  * cost_out [S], grad_out [S][6] (J^T r), JtJ_out [S][36] (row-major P x P in the top-left).
  * workspace: [dev] at least frustum_evaluate_workspace_bytes(S, n_stride) bytes. */
@@ -197,7 +202,8 @@ int ball_query_forward(const float* dist, float radius, int32_t* out,
 /* Coordinate-based variant: same output contract as ball_query_forward, computed with a
  * uniform grid hash from  points [B][3][N] f32  and  nodes [B][3][M] f32  (channel-first, as
  * models/networks_pc.py:47-65 holds them) -- the dense B x M x N distance matrix is never built.
- * hit <=> ((dx*dx + dy*dy) + dz*dz) <= radius*radius in float32 without fma.  N <= 65536.
+ * hit <=> ((dx*dx + dy*dy) + dz*dz) <= radius*radius in float32 without fma -- a contract on SQUARED distances (the
+ * reference thresholds the rounded square root; they can differ within one ulp of the radius).  N <= 65536.
  * workspace: [dev], 16-byte aligned, >= ball_query_xyz_workspace_bytes(B, N). */
 size_t ball_query_xyz_workspace_bytes(int B, int N);
 int ball_query_xyz_forward(const float* points, const float* nodes, float radius, int32_t* out, int B, int M, int N,
@@ -211,7 +217,8 @@ int ball_query_xyz_forward(const float* points, const float* nodes, float radius
  *   min_idx   [B][N]    i32  = min_k_idx[..][0], the `index` argument of index_max (:65,:88-90)
  *   count     [B][M]    i32  points per node (mask_row_sum, :69-72; mask_row_max = count > 0)
  *   cluster_mean [B][3][M] f32 = float(sum_fixed * 2^-24) / (float(count) + 1e-5f), sum_fixed = exact int64 sum
- *                            of rint(x * 2^24) -- order independent (:74-76)
+ *                            of rint(x * 2^24) -- order independent (:74-76); points with a non-finite coordinate are
+ *                            left out of count and sums (they still get min_idx 0)
  *   pc_centers, pc_decentered [B][3][N] f32 (each may be NULL): cluster_mean gathered by min_idx, pc - centers (:78-82)
  * 1 <= k <= min(8, M), M <= 2048.  workspace: [dev], 8-byte aligned, >= cluster_assign_workspace_bytes(B, M). */
 size_t cluster_assign_workspace_bytes(int B, int M);

@@ -288,11 +288,12 @@ def cluster_assign(pc, node, k):
     min_idx = order[:, :, 0]
     count = np.zeros((B, M), dtype=np.int32)
     sums = np.zeros((B, 3, M), dtype=np.int64)
-    fixed = np.rint(p.astype(np.float64) * 16777216.0).astype(np.int64)
+    finite = np.isfinite(p).all(axis=1)                           # non-finite points join no count / sum
+    fixed = np.rint(np.where(finite[:, None, :], p, 0).astype(np.float64) * 16777216.0).astype(np.int64)
     for b in range(B):
-        np.add.at(count[b], min_idx[b], 1)
+        np.add.at(count[b], min_idx[b][finite[b]], 1)
         for a in range(3):
-            np.add.at(sums[b, a], min_idx[b], fixed[b, a])
+            np.add.at(sums[b, a], min_idx[b][finite[b]], fixed[b, a][finite[b]])
     num = (sums.astype(np.float64) * (1.0 / 16777216.0)).astype(np.float32)
     mean = num / (count.astype(np.float32)[:, None, :] + np.float32(1e-5))
     centers = np.take_along_axis(mean, np.broadcast_to(min_idx[:, None, :].astype(np.int64), (B, 3, N)), axis=2)

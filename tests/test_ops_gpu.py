@@ -120,6 +120,49 @@ def test_golden_index_max(cuda):
         np.testing.assert_array_equal(run_index_max(z["data"], z["index"], int(z["K"])), z["out"])
 
 
+def test_index_max_queue_overflow_and_ties(cuda):
+    """Ascending data makes EVERY element a new running maximum (the filter passes everything, the per-warp candidate
+    queues overflow and the in-place path is taken); constant data makes every element a tie (lowest n must win)."""
+    B, C, N, K = 2, 5, 8192, 16
+    rng = np.random.default_rng(5)
+    index = rng.integers(0, K, (B, N), dtype=np.int32)
+    data = np.empty((B, C, N), dtype=np.float32)
+    data[:, 0] = np.arange(N, dtype=np.float32)[None]               # ascending: last element of each segment wins
+    data[:, 1] = -np.arange(N, dtype=np.float32)[None]              # descending: first element wins
+    data[:, 2] = 3.25                                               # all ties: lowest n wins
+    data[:, 3] = np.repeat(np.arange(N // 64, dtype=np.float32), 64)[None]   # plateaus of 64 equal values
+    data[:, 4] = rng.standard_normal((B, N), dtype=np.float32)
+    np.testing.assert_array_equal(run_index_max(data, index, K), oracle.index_max(data, index, K))
+
+
+def test_index_max_dropin_cpu_entry_points(cuda):
+    """forward_cpu / forward_multi_thread_cpu keep the reference's CPU-tensor contract (index_max.cpp:73-112) and
+    reproduce the fixtures written by the reference's own forward_cpu."""
+    import importlib
+    im = importlib.import_module("deepi2p_b200.dropin.index_max")
+    for f in sorted(glob.glob(os.path.join(GOLDEN, "index_max_*.npz"))):
+        z = np.load(f)
+        d, i, K = torch.from_numpy(z["data"]), torch.from_numpy(z["index"]), int(z["K"])
+        for out in (im.forward_cpu(d, i, K), im.forward_multi_thread_cpu(d, i, K, 8)):
+            assert out.device.type == "cpu" and out.dtype == torch.int32
+            np.testing.assert_array_equal(out.numpy(), z["out"])
+    with pytest.raises(RuntimeError):
+        im.forward_cpu(torch.zeros(1, 1, 4, device="cuda"), torch.zeros(1, 4, dtype=torch.int32, device="cuda"), 2)
+
+
+def test_ball_query_later_quarters_stop_early(cuda):
+    """Rows whose first quarter already holds K hits: later quarters stop loading once the running counts say so, and
+    whatever they had collected must not leak into the output."""
+    B, M, N, K = 1, 4, 32768, 32
+    dist = np.full((B, M, N), 9.0, dtype=np.float32)
+    dist[0, 0, :K] = 0.0; dist[0, 0, N // 2:] = 0.0                 # K hits at once, then half the row hits
+    dist[0, 1, 100:100 + 2 * K] = 0.0; dist[0, 1, -5:] = 0.0        # > K early, a few at the very end
+    dist[0, 2, ::1024] = 0.0                                        # exactly 32 hits spread over all quarters
+    dist[0, 3, N // 4 - 3:N // 4 + 3] = 0.0                         # 6 hits straddling the first boundary
+    got = run_ball_query(dist, 1.0, K)
+    np.testing.assert_array_equal(got, oracle.ball_query(dist, 1.0, K))
+
+
 def _load_ref(name):
     import importlib.util
     ref_dir = os.path.join(os.path.dirname(GOLDEN), "..", "oracle", "_ref")

@@ -214,8 +214,11 @@ def main():
         pf, lf = per[s]
         xs, ls_, ns_ = prep["xyz"][s:s + 1], prep["label"][s:s + 1], prep["n_pts"][s:s + 1]
 
-        def ext(x6, xs=xs, ls_=ls_, ns_=ns_):
-            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d)
+        calls = [0]
+
+        def ext(x6, xs=xs, ls_=ls_, ns_=ns_, calls=calls):
+            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d, pass_index=calls[0])
+            calls[0] += 1                 # the oracle evaluates in the same order as the kernel counts its passes
             return float(c[0]), gr[0].cpu().numpy(), A[0].cpu().numpy()
 
         o = oracle.solve(pf, lf, K, inits[s, i, 0], inits[s, i, 1:4], H, W, syn.T_LB, syn.T_UB, 500, is_2d,
