@@ -434,6 +434,8 @@ def main():
             kern_ms.append(stimer.ms())
             tl = frustum.last_solve_timeline(dev, register_shape=(S_local, n_inits, n_points))
             tails.append((tl[2] - tl[1]) * 1e-6)
+            ce = frustum.last_solve_cta_end_times(dev, register_shape=(S_local, n_inits, n_points))
+            cta_tail = ((ce.astype(np.float64) - float(tl[1])) * 1e-6) if ce is not None and len(ce) else np.zeros(1)
     sampler.mark_end()
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
@@ -563,6 +565,9 @@ def main():
                              "(dib_profile_solve_events), rank 0; ms_per_step is the max over ranks",
             "tail_ms": sum(tails) / len(tails),
             "tail_note": "queue empty -> last CTA exit, from the kernel's own globaltimer words",
+            "cta_exit_after_queue_empty_ms": {"p10": float(np.percentile(cta_tail, 10)), "p50": float(np.percentile(cta_tail, 50)),
+                                              "p90": float(np.percentile(cta_tail, 90)), "max": float(cta_tail.max()),
+                                              "mean": float(cta_tail.mean()), "ctas": int(cta_tail.size)},
             "point_evals_per_s": pts_evals / args.steps / (k_ms * 1e-3),
             "mean_cloud_passes_per_solve": passes_mean, "mean_lm_iterations_per_solve": iters_mean,
             "compulsory_bytes_per_launch": compulsory,

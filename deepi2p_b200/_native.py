@@ -11,7 +11,7 @@ _c = ctypes
 _lib = None
 
 EXPORTS = (
-    "dib_abi_version", "dib_last_error", "dib_device_sm_count", "dib_profile_solve_events", "dib_evaluate_pass_index",
+    "dib_abi_version", "dib_last_error", "dib_device_sm_count", "dib_profile_solve_events", "dib_evaluate_sliced", "frustum_solve_slice_after",
     "frustum_solve_workspace_bytes", "frustum_solve_batch_f32", "frustum_solve_batch_f64", "frustum_solve_traced_f32",
     "frustum_register_workspace_bytes", "frustum_register_batch_f32",
     "frustum_evaluate_workspace_bytes",
@@ -65,8 +65,10 @@ def load():
                           "rebuild with `python -m deepi2p_b200.build --force`")
     lib.dib_last_error.restype = _c.c_char_p
     lib.dib_device_sm_count.restype = i32
-    lib.dib_evaluate_pass_index.restype = None
-    lib.dib_evaluate_pass_index.argtypes = [i32]
+    lib.dib_evaluate_sliced.restype = None
+    lib.dib_evaluate_sliced.argtypes = [i32]
+    lib.frustum_solve_slice_after.restype = i32
+    lib.frustum_solve_slice_after.argtypes = [i32, i32, i32, i32]
     lib.dib_profile_solve_events.restype = None
     lib.dib_profile_solve_events.argtypes = [vp, vp]
     lib.frustum_solve_workspace_bytes.restype = sz

@@ -619,7 +619,7 @@ struct WarpScratch {
 // touched by the owner only.
 template <typename CT, int P>
 struct ProbCtx {
-  double part[kMaxSlices][NAcc<P>::N];    // slice sums of the open pass (line-search scratch between passes)
+  double part[kMaxSlices][NAcc<P>::N];    // slice sums of the open pass
   double tot[NAcc<P>::N];
   PoseConst pose;
   ClassConst cls;
@@ -633,7 +633,6 @@ struct ProbCtx {
   int next_slice;                         // claim counter of the open pass (>= nslices: nothing left to claim)
   int done;                               // slices of the open pass that are finished
 };
-static_assert(kMaxSlices * NAcc<4>::N >= 72, "part[] doubles as the 72-double line-search scratch");
 
 template <typename CT, int P>
 struct Smem {
@@ -888,194 +887,235 @@ __device__ __forceinline__ bool chol_solve(const double (&As)[P][P], const doubl
   return ok;
 }
 
-__device__ double poly_eval(const double* p, int n, double x) {   // n coefficients, highest first
-  double v = 0.0;
-  #pragma unroll 1
-  for (int i = 0; i < n; ++i) v = v * x + p[i];
-  return v;
-}
+// ------------------------------------------------------------------------------------------
+// Warp-collective line-search interpolation (every lane of the warp calls; the result is warp-uniform).
+//
+// Same algorithm as before -- the polynomial through the line-search samples from a full-pivot elimination of the
+// Vandermonde-type system, its minimum over [xmin, xmax] from the real parts of ALL roots of the derivative, roots of
+// cubics / quartics by Durand-Kerner -- but spread over the lanes: lane r holds row r of the system, a pivot search is
+// a shuffle reduction with the serial scan's tie rule (first maximum in row-major order), row operations run in
+// parallel, and every root of the derivative is iterated by its own lane (total-step Durand-Kerner: all roots are
+// updated from the previous iterate).  The control step of a pass is on the critical path of its problem, and as
+// straight-line single-lane code it was also ~50 KB of instructions that every problem dragged through the
+// instruction cache once per pass; this version is ~4x shorter in both respects.
+// ------------------------------------------------------------------------------------------
+constexpr unsigned kFull = 0xffffffffu;
 
-__device__ double ipow(double x, int k) {
-  double v = 1.0;
-  #pragma unroll 1
-  for (int i = 0; i < k; ++i) v *= x;
-  return v;
-}
-
-// Durand-Kerner iteration for a polynomial of exact degree DEG (coefficients highest first, p[0] != 0).
-// Everything lives in registers (fully unrolled); returns DEG real parts.
-template <int DEG>
-__device__ __noinline__ int durand_kerner(const double* p, double* roots) {
-  double c[DEG + 1], zr[DEG], zi[DEG];
-  const double ip0 = 1.0 / p[0];
-#pragma unroll
-  for (int i = 0; i <= DEG; ++i) c[i] = p[i] * ip0;
+// Roots (real parts) of the monic polynomial c[0..deg], deg in {3, 4}, into roots[0..deg).
+__device__ __forceinline__ void durand_kerner_warp(const double (&c)[5], int deg, double (&roots)[4], int lane) {
   // Fujiwara's bound on the root moduli: 2 max_k |c_k|^(1/k) (the last coefficient halved)
   double radius = 0.0;
 #pragma unroll
-  for (int i = 1; i <= DEG; ++i) {
-    const double a = fabs(c[i]) * (i == DEG ? 0.5 : 1.0);
-    radius = fmax(radius, a > 0.0 ? exp(log(a) / (double)i) : 0.0);
+  for (int i = 1; i <= 4; ++i) {
+    if (i <= deg) {
+      const double a = fabs(c[i]) * (i == deg ? 0.5 : 1.0);
+      radius = fmax(radius, a > 0.0 ? exp(log(a) / (double)i) : 0.0);
+    }
   }
   radius = 2.0 * radius + 1e-300;
-  // start points on the circle of half that radius, fixed phases (cos/sin of 2 pi i / DEG + 0.4)
-#pragma unroll
-  for (int i = 0; i < DEG; ++i) {
-    double s, co;
-    sincos(2.0 * 3.14159265358979323846 * i / DEG + 0.4, &s, &co);
-    zr[i] = 0.5 * radius * co; zi[i] = 0.5 * radius * s;
-  }
+  const int me = lane % deg;                      // every aligned group of 4 lanes holds all the roots
+  double s, co;
+  sincos(2.0 * 3.14159265358979323846 * me / deg + 0.4, &s, &co);   // start points on the circle of half that radius
+  double zr = 0.5 * radius * co, zi = 0.5 * radius * s;
 #pragma unroll 1
   for (int it = 0; it < 100; ++it) {
-    double change = 0.0;
+    double nr = 0.0, ni = 0.0;                    // p(z) by Horner
 #pragma unroll
-    for (int i = 0; i < DEG; ++i) {
-      double nr = 0.0, ni = 0.0;
-#pragma unroll
-      for (int k = 0; k <= DEG; ++k) {
-        const double tr = nr * zr[i] - ni * zi[i] + c[k];
-        const double ti = nr * zi[i] + ni * zr[i];
+    for (int k = 0; k <= 4; ++k) {
+      if (k <= deg) {
+        const double tr = nr * zr - ni * zi + c[k];
+        const double ti = nr * zi + ni * zr;
         nr = tr; ni = ti;
       }
-      double dr = 1.0, di = 0.0;
-#pragma unroll
-      for (int j = 0; j < DEG; ++j) if (j != i) {
-        const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
-        const double tr = dr * er - di * ei, ti = dr * ei + di * er;
-        dr = tr; di = ti;
-      }
-      double den = dr * dr + di * di;
-      if (den == 0.0) { dr = 1e-300; di = 0.0; den = dr * dr; if (den == 0.0) den = 1e-300; }
-      const double iden = 1.0 / den;
-      const double qr = (nr * dr + ni * di) * iden, qi = (ni * dr - nr * di) * iden;
-      zr[i] -= qr; zi[i] -= qi;
-      change = fmax(change, sqrt(qr * qr + qi * qi));
     }
+    double dr = 1.0, di = 0.0;                    // prod over the other roots of (z - z_j), j ascending
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (j < deg) {
+        const double zrj = __shfl_sync(kFull, zr, j), zij = __shfl_sync(kFull, zi, j);
+        if (j != me) {
+          const double er = zr - zrj, ei = zi - zij;
+          const double tr = dr * er - di * ei, ti = dr * ei + di * er;
+          dr = tr; di = ti;
+        }
+      }
+    }
+    double den = dr * dr + di * di;
+    if (den == 0.0) { dr = 1e-300; di = 0.0; den = dr * dr; if (den == 0.0) den = 1e-300; }
+    const double iden = 1.0 / den;
+    const double qr = (nr * dr + ni * di) * iden, qi = (ni * dr - nr * di) * iden;
+    zr -= qr; zi -= qi;
+    double change = sqrt(qr * qr + qi * qi);
+    change = fmax(change, __shfl_xor_sync(kFull, change, 1));
+    change = fmax(change, __shfl_xor_sync(kFull, change, 2));
     if (change < 1e-14 * radius) break;
   }
 #pragma unroll
-  for (int i = 0; i < DEG; ++i) roots[i] = zr[i];
-  return DEG;
+  for (int i = 0; i < 4; ++i) roots[i] = __shfl_sync(kFull, zr, i);
 }
 
-// Real parts of all roots of p (n coefficients, highest first; n - 1 <= 4).
-__device__ __noinline__ int poly_roots_real(const double* pin, int n, double* roots) {
-  double p[6];
-  int lead = 0;
-  #pragma unroll 1
-  while (lead < n && pin[lead] == 0.0) ++lead;
-  const int m = n - lead;
-  #pragma unroll 1
-  for (int i = 0; i < m; ++i) p[i] = pin[lead + i];
-  const int deg = m - 1;
-  if (deg <= 0) return 0;
-  if (deg == 1) { roots[0] = -p[1] / p[0]; return 1; }
-  if (deg == 2) {
-    const double a = p[0], b = p[1], c = p[2];
+// Step size minimising the polynomial that interpolates the line-search samples over [xmin, xmax] (cubic
+// interpolation: values and gradients of lower / current / previous).
+//
+// The nc x nc system (nc <= 6) lives in the lanes: lane l holds M[l >> 3][l & 7] (rows 0..3) and, for l < 16,
+// M[4 + (l >> 3)][l & 7] (rows 4, 5); column 6 is the right-hand side.  Every row operation of the serial full-pivot
+// elimination is then one or two instructions for all elements at once, with the pivot row / column read by shuffles,
+// and the loops over k are real loops (small code).  The arithmetic per element is that of the serial algorithm.
+__device__ __forceinline__ double mat_fetch(double e0, double e1, int i, int j) {
+  const int src = ((i & 3) << 3) | j;
+  const double v0 = __shfl_sync(kFull, e0, src), v1 = __shfl_sync(kFull, e1, src);
+  return i < 4 ? v0 : v1;
+}
+
+__device__ __noinline__ double interp_min_step_warp(const LsSample& lower, const LsSample& previous, const LsSample& current,
+                                                    double xmin, double xmax, int lane) {
+  if (!current.value_valid) return fmin(fmax(current.x * 0.5, xmin), xmax);
+  const LsSample* smp[3] = {&lower, &current, &previous};
+  const int ns = previous.value_valid ? 3 : 2;
+  int nc = 0;
+#pragma unroll 1
+  for (int i = 0; i < ns; ++i) { nc += smp[i]->value_valid ? 1 : 0; nc += smp[i]->gradient_valid ? 1 : 0; }
+  const int deg = nc - 1;
+  const int j = lane & 7, i0 = lane >> 3, i1 = 4 + (lane >> 3);
+  // element of row `r`, column j: value rows x^deg .. x^0, gradient rows deg x^(deg-1) .. 1 0, column 6 = rhs
+  auto element = [&](int r) -> double {
+    if (r >= nc || j == 7) return 0.0;
+    int row = 0, kind = -1;
+    double sx = 0.0, rhs = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < ns; ++i) {
+      if (smp[i]->value_valid) { if (row == r) { sx = smp[i]->x; rhs = smp[i]->value; kind = 0; } ++row; }
+      if (smp[i]->gradient_valid) { if (row == r) { sx = smp[i]->x; rhs = smp[i]->gradient; kind = 1; } ++row; }
+    }
+    if (j == 6) return rhs;
+    const int e = (kind == 0) ? deg - j : deg - j - 1;      // exponent of x in this entry
+    if (e < 0) return 0.0;
+    double pw = 1.0;                                       // x^e by repeated multiplication
+#pragma unroll 1
+    for (int q = 0; q < e; ++q) pw = pw * sx;
+    return (kind == 0) ? pw : (double)(e + 1) * pw;
+  };
+  double e0 = element(i0), e1 = (lane < 16) ? element(i1) : 0.0;
+
+  // full-pivot elimination (column permutation packed in one register, 4 bits per entry)
+  unsigned perm = 0x543210u;
+#pragma unroll 1
+  for (int k = 0; k < nc; ++k) {
+    // pivot: first maximum of |M[i][j]| over i, j in [k, nc) in row-major order
+    double val = -1.0;
+    int idx = 0x7fffffff;
+    if (j >= k && j < nc) {
+      if (i0 >= k && i0 < nc) { val = fabs(e0); idx = i0 * 8 + j; if (!(val > -1.0)) { val = -1.0; } }
+      if (lane < 16 && i1 >= k && i1 < nc) {
+        const double v1 = fabs(e1);
+        if (v1 > val) { val = v1; idx = i1 * 8 + j; }
+        else if (idx == 0x7fffffff) idx = i1 * 8 + j;
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const double ov = __shfl_xor_sync(kFull, val, o);
+      const int oi = __shfl_xor_sync(kFull, idx, o);
+      if (ov > val || (ov == val && oi < idx)) { val = ov; idx = oi; }
+    }
+    if (val < 0.0) idx = k * 8 + k;                 // nothing comparable (NaNs): the serial scan keeps (k, k)
+    if (val == 0.0) {                               // singular: remaining right-hand sides are zeroed, elimination stops
+      if (j == 6) { if (i0 >= k && i0 < nc) e0 = 0.0; if (lane < 16 && i1 >= k && i1 < nc) e1 = 0.0; }
+      break;
+    }
+    const int pr = idx >> 3, pcv = idx & 7;
+    if (pr != k) {                                  // row swap (all columns and the rhs)
+      const double ak0 = mat_fetch(e0, e1, k, j), ap0 = mat_fetch(e0, e1, pr, j);
+      if (i0 == k) e0 = ap0; else if (i0 == pr) e0 = ak0;
+      if (i1 == k) e1 = ap0; else if (i1 == pr) e1 = ak0;
+    }
+    if (pcv != k) {                                 // column swap (all rows)
+      const int jo = (j == k) ? pcv : ((j == pcv) ? k : j);
+      const double n0 = __shfl_sync(kFull, e0, (i0 << 3) | jo), n1 = __shfl_sync(kFull, e1, (i0 << 3) | jo);
+      e0 = n0; e1 = n1;
+      const unsigned pa = (perm >> (4 * pcv)) & 15u, pb = (perm >> (4 * k)) & 15u;
+      perm = (perm & ~((15u << (4 * pcv)) | (15u << (4 * k)))) | (pb << (4 * pcv)) | (pa << (4 * k));
+    }
+    // M[i][j] -= (M[i][k] / M[k][k]) M[k][j] for i > k, j >= k (rhs included)
+    const double pkk = mat_fetch(e0, e1, k, k);
+    const double pkj = mat_fetch(e0, e1, k, j);
+    const double a0 = __shfl_sync(kFull, e0, (i0 << 3) | k), a1 = __shfl_sync(kFull, e1, (i0 << 3) | k);
+    if (j >= k && (j < nc || j == 6)) {
+      if (i0 > k && i0 < nc) { const double f = a0 / pkk; e0 -= f * pkj; }
+      if (lane < 16 && i1 > k && i1 < nc) { const double f = a1 / pkk; e1 -= f * pkj; }
+    }
+  }
+  // back substitution: z[k] kept by lane k
+  double zmine = 0.0;
+#pragma unroll 1
+  for (int k = nc - 1; k >= 0; --k) {
+    const double mkk = mat_fetch(e0, e1, k, k);
+    double sacc = mat_fetch(e0, e1, k, 6);
+#pragma unroll 1
+    for (int jj = k + 1; jj < nc; ++jj) sacc -= mat_fetch(e0, e1, k, jj) * __shfl_sync(kFull, zmine, jj);
+    const double zk = (mkk == 0.0) ? 0.0 : sacc / mkk;
+    if (lane == k) zmine = zk;
+  }
+  // poly[perm[k]] = z[k]; coefficient c of the polynomial kept by lane c (highest power first)
+  double pmine = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < nc; ++k) {
+    const double zk = __shfl_sync(kFull, zmine, k);
+    if (lane == (int)((perm >> (4 * k)) & 15u)) pmine = zk;
+  }
+  auto poly_at = [&](double x) -> double {
+    double v = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < nc; ++i) v = v * x + __shfl_sync(kFull, pmine, i);
+    return v;
+  };
+  double best_x = (xmin + xmax) / 2.0;
+  double best_v = poly_at(best_x);
+  const double vmin = poly_at(xmin);
+  if (vmin < best_v) { best_v = vmin; best_x = xmin; }
+  const double vmax = poly_at(xmax);
+  if (vmax < best_v) { best_v = vmax; best_x = xmax; }
+  if (nc <= 2) return best_x;
+  // derivative (deg coefficients, lane jj holds coefficient jj), leading zeros stripped
+  const double dmine = (lane < deg) ? (double)(deg - lane) * pmine : 0.0;
+  const unsigned zmask = __ballot_sync(kFull, lane < deg && dmine == 0.0);
+  int lead = __ffs(~zmask) - 1;
+  if (lead > deg) lead = deg;
+  const double qmine = __shfl_sync(kFull, dmine, (lane + lead) & 31);     // q[i] = der[lead + i]
+  const int rdeg = deg - lead - 1;
+  double roots[4] = {0.0, 0.0, 0.0, 0.0};
+  int nr = 0;
+  if (rdeg == 1) {
+    roots[0] = -__shfl_sync(kFull, qmine, 1) / __shfl_sync(kFull, qmine, 0);
+    nr = 1;
+  } else if (rdeg == 2) {
+    const double a = __shfl_sync(kFull, qmine, 0), b = __shfl_sync(kFull, qmine, 1), c = __shfl_sync(kFull, qmine, 2);
     const double D = b * b - 4 * a * c;
     const double sD = sqrt(fabs(D));
     if (D >= 0) {
       if (b >= 0) { roots[0] = (-b - sD) / (2.0 * a); roots[1] = (2.0 * c) / (-b - sD); }
       else { roots[0] = (2.0 * c) / (-b + sD); roots[1] = (-b + sD) / (2.0 * a); }
     } else { roots[0] = -b / (2.0 * a); roots[1] = roots[0]; }
-    return 2;
+    nr = 2;
+  } else if (rdeg >= 3) {
+    const double ip0 = 1.0 / __shfl_sync(kFull, qmine, 0);
+    double c[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) c[i] = __shfl_sync(kFull, qmine, i) * ip0;
+    durand_kerner_warp(c, rdeg, roots, lane);
+    nr = rdeg;
   }
-  // Durand-Kerner on the monic polynomial (all roots, complex), register-resident for the
-  // quartic that the 3-sample interpolation produces; DEG is a compile-time bound.
-  if (deg == 4) return durand_kerner<4>(p, roots);
-  return durand_kerner<3>(p, roots);
-}
-
-// Step size minimising the polynomial that interpolates the line-search samples over
-// [xmin, xmax] (cubic interpolation: values and gradients of lower / current / previous).
-// `scratch` (>= 72 doubles, shared memory): the dynamically indexed 6x6 system must not live in
-// local memory, whose lines get evicted from L1 by the streaming loads (long-scoreboard stalls).
-__device__ __noinline__ double interpolating_min_step(const LsSample& lower, const LsSample& previous, const LsSample& current,
-                                         double xmin, double xmax, double* scratch) {
-  if (!current.value_valid) return fmin(fmax(current.x * 0.5, xmin), xmax);
-  const LsSample* s[3] = {&lower, &current, &previous};
-  const int ns = previous.value_valid ? 3 : 2;
-  int nc = 0;
-  #pragma unroll 1
-  for (int i = 0; i < ns; ++i) { if (s[i]->value_valid) ++nc; if (s[i]->gradient_valid) ++nc; }
-  const int deg = nc - 1;
-  double (*M)[6] = reinterpret_cast<double (*)[6]>(scratch);   // [6][6]
-  double* rhs = scratch + 36;
-  double* poly = scratch + 42;
-  double* z = scratch + 48;
-  double* der = scratch + 54;
-  double* roots = scratch + 60;
-  double* pw = scratch + 66;
-  #pragma unroll 1
-  for (int i = 0; i < 6; ++i) { rhs[i] = 0; poly[i] = 0; for (int j = 0; j < 6; ++j) M[i][j] = 0; }
-  int row = 0;
-  #pragma unroll 1
-  for (int i = 0; i < ns; ++i) {
-    pw[0] = 1.0;                        // pw[k] = x^k by repeated multiplication
-    #pragma unroll 1
-    for (int k = 1; k <= deg; ++k) pw[k] = pw[k - 1] * s[i]->x;
-    if (s[i]->value_valid) {
-      #pragma unroll 1
-      for (int j = 0; j <= deg; ++j) M[row][j] = pw[deg - j];
-      rhs[row] = s[i]->value; ++row;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i < nr && !(roots[i] < xmin || roots[i] > xmax)) {
+      const double v = poly_at(roots[i]);
+      if (v < best_v) { best_v = v; best_x = roots[i]; }
     }
-    if (s[i]->gradient_valid) {
-      #pragma unroll 1
-      for (int j = 0; j < deg; ++j) M[row][j] = (deg - j) * pw[deg - j - 1];
-      rhs[row] = s[i]->gradient; ++row;
-    }
-  }
-  // full-pivot elimination (column permutation packed in one register, 4 bits per entry)
-  unsigned perm = 0x543210u;
-  #pragma unroll 1
-  for (int k = 0; k < nc; ++k) {
-    int pr = k, pcv = k; double best = -1.0;
-    #pragma unroll 1
-    for (int i = k; i < nc; ++i) for (int j = k; j < nc; ++j)
-      if (fabs(M[i][j]) > best) { best = fabs(M[i][j]); pr = i; pcv = j; }
-    if (best == 0.0) { for (int i = k; i < nc; ++i) rhs[i] = 0.0; break; }
-    if (pr != k) { for (int j = 0; j < nc; ++j) { double t = M[pr][j]; M[pr][j] = M[k][j]; M[k][j] = t; } double t = rhs[pr]; rhs[pr] = rhs[k]; rhs[k] = t; }
-    if (pcv != k) { for (int i = 0; i < nc; ++i) { double t = M[i][pcv]; M[i][pcv] = M[i][k]; M[i][k] = t; } const unsigned pa = (perm >> (4 * pcv)) & 15u, pb = (perm >> (4 * k)) & 15u;
-                    perm = (perm & ~((15u << (4 * pcv)) | (15u << (4 * k)))) | (pb << (4 * pcv)) | (pa << (4 * k)); }
-    #pragma unroll 1
-    for (int i = k + 1; i < nc; ++i) {
-      const double f = M[i][k] / M[k][k];
-      #pragma unroll 1
-      for (int j = k; j < nc; ++j) M[i][j] -= f * M[k][j];
-      rhs[i] -= f * rhs[k];
-    }
-  }
-  #pragma unroll 1
-  for (int k = nc - 1; k >= 0; --k) {
-    if (M[k][k] == 0.0) { z[k] = 0.0; continue; }
-    double sacc = rhs[k];
-    #pragma unroll 1
-    for (int j = k + 1; j < nc; ++j) sacc -= M[k][j] * z[j];
-    z[k] = sacc / M[k][k];
-  }
-  #pragma unroll 1
-  for (int k = 0; k < nc; ++k) poly[(perm >> (4 * k)) & 15u] = z[k];
-
-  double best_x = (xmin + xmax) / 2.0;
-  double best_v = poly_eval(poly, nc, best_x);
-  const double vmin = poly_eval(poly, nc, xmin);
-  if (vmin < best_v) { best_v = vmin; best_x = xmin; }
-  const double vmax = poly_eval(poly, nc, xmax);
-  if (vmax < best_v) { best_v = vmax; best_x = xmax; }
-  if (nc <= 2) return best_x;
-  #pragma unroll 1
-  for (int j = 0; j < deg; ++j) der[j] = (deg - j) * poly[j];
-  const int nr = poly_roots_real(der, deg, roots);
-  #pragma unroll 1
-  for (int i = 0; i < nr; ++i) {
-    if (roots[i] < xmin || roots[i] > xmax) continue;
-    const double v = poly_eval(poly, nc, roots[i]);
-    if (v < best_v) { best_v = v; best_x = roots[i]; }
   }
   return best_x;
 }
 
-enum { LM_DONE = 0, LM_EVAL = 1 };
+enum { LM_DONE = 0, LM_EVAL = 1, LM_INTERP = 2 };
 
 // Starts the next trust-region iteration(s) until an evaluation is needed or the solve ends.
 template <int P>
@@ -1190,9 +1230,13 @@ __device__ __noinline__ int lm_after_candidate(LMState<P>& st, const double* tot
   return lm_next_step<P>(st);
 }
 
-// Consumes the evaluation at st.xt (totals in tot).  Returns LM_EVAL with a new st.xt or LM_DONE.
 template <int P>
-__device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot, double* scratch) {
+__device__ __noinline__ int lm_consume_step(LMState<P>& st, double a, bool fail);
+
+// Consumes the evaluation at st.xt (totals in tot).  Returns LM_EVAL with a new st.xt, LM_DONE, or LM_INTERP when the
+// line search needs an interpolated step size (interp_min_step_warp, then lm_consume_step).
+template <int P>
+__device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot) {
   constexpr int NA = NAcc<P>::NA;
   if (st.phase == 3) {                     // infeasible start: Problem::Evaluate at the untouched init, no solve
     st.cost = tot[0];
@@ -1228,12 +1272,19 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot, double
     }
     ++st.ls_iter;
     ++st.ls_steps;
-    bool fail = st.ls_iter >= 20;
-    double a = 0.0;
-    if (!fail) {
-      a = interpolating_min_step(st.lower, st.prev, cur, 1e-3 * cur.x, 0.6 * cur.x, scratch);
-      if (a * st.dmax < 1e-9) fail = true;
-    }
+    if (st.ls_iter < 20) return LM_INTERP;    // the warp computes the interpolated step, then lm_consume_step() goes on
+    return lm_consume_step<P>(st, 0.0, true);
+  }
+  return lm_after_candidate<P>(st, tot);
+}
+
+// Second half of a failed Armijo test: `a` is the step size from the warp-collective interpolation (or `fail` is set
+// because the line search ran out of iterations).
+template <int P>
+__device__ __noinline__ int lm_consume_step(LMState<P>& st, double a, bool fail) {
+  {
+    LsSample& cur = st.cur;
+    if (!fail && a * st.dmax < 1e-9) fail = true;
     if (fail) {
       // line search failed: the full step is the candidate (delta untouched)
       project_plus<P>(st, st.x, st.delta, 1.0, st.xt);
@@ -1250,7 +1301,6 @@ __device__ __noinline__ int lm_consume(LMState<P>& st, const double* tot, double
     }
     return LM_EVAL;
   }
-  return lm_after_candidate<P>(st, tot);
 }
 
 // Sets st.xt and returns LM_EVAL (an infeasible start asks for ONE cost-only pass at the init, phase 3).
@@ -1309,6 +1359,8 @@ struct SolveArgs {
   int trace_cap;
 };
 
+constexpr int kCtaEndSlots = 1024;   // per-CTA exit times kept after the workspace header (benchmark timeline)
+constexpr size_t kHeaderBytes = 256 + kCtaEndSlots * 8;
 constexpr int kTraceRec = 16;   // doubles per trace record, see include/deepi2p_b200.h (frustum_solve_traced_*)
 
 // Scheduling order.  Solve length correlates with how far an init's heading is from the centre of its
@@ -1401,6 +1453,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
   // Launch timeline for the benchmark (three 64-bit words after the queue counter, zeroed / primed by the host):
   // kernel start, the moment the queue ran dry, the last CTA's exit -- all in globaltimer nanoseconds.
   unsigned long long* tl = reinterpret_cast<unsigned long long*>(a.queue) + 1;
+  unsigned long long* cta_end = reinterpret_cast<unsigned long long*>(a.queue) + 32;   // [kCtaEndSlots], after the 256-byte header
   if (threadIdx.x == 0) atomicMin(tl + 0, global_ns());
   __syncthreads();                               // the only CTA-wide barrier of the kernel
   const int total = a.S * a.I;
@@ -1483,7 +1536,16 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         int rc = LM_DONE;
         if (lane == 0) {
           trace_record<CT, P>(a, me, n_rec, false);
-          rc = lm_consume<P>(me.lm, me.tot, &me.part[0][0]);
+          rc = lm_consume<P>(me.lm, me.tot);
+        }
+        __syncwarp();
+        rc = __shfl_sync(0xffffffffu, rc, 0);
+        if (rc == LM_INTERP) {                      // warp-collective: interpolated line-search step size
+          const LMState<P>& st = me.lm;
+          const double step = interp_min_step_warp(st.lower, st.prev, st.cur, 1e-3 * st.cur.x, 0.6 * st.cur.x, lane);
+          if (lane == 0) rc = lm_consume_step<P>(me.lm, step, false);
+        }
+        if (lane == 0) {
           trace_record<CT, P>(a, me, n_rec, true);
           ++n_rec;
           if (rc == LM_EVAL) {
@@ -1532,7 +1594,11 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
           if (lane == 0) na = ld_volatile(&sm.n_active);
           na = __shfl_sync(0xffffffffu, na, 0);
           if (na == 0) {                         // every problem of this CTA is finished
-            if (lane == 0) atomicMax(tl + 2, global_ns());
+            if (lane == 0) {
+              const unsigned long long t_end = global_ns();
+              atomicMax(tl + 2, t_end);
+              if (blockIdx.x < kCtaEndSlots) atomicMax(cta_end + blockIdx.x, t_end);     // the CTA's last warp wins
+            }
             break;
           }
         }
@@ -1713,6 +1779,15 @@ static int default_slice_after() {
   return v;
 }
 
+// Passes of a problem that run as one slice before the fixed slicing starts.  A batch that keeps every warp of the
+// machine busy for several waves uses DIB_SLICE_AFTER (only the long solves, i.e. the tail, pay for being helpable); a
+// batch with fewer problems than ~4 waves has idle warps from the start, so its passes are sliced from the first one.
+// (The two settings give sums that differ at rounding level; a given call is deterministic.)
+static int slice_after_for(long long total_problems, long long resident_warps) {
+  if (getenv("DIB_SLICE_AFTER")) return default_slice_after();
+  return total_problems >= 4 * resident_warps ? default_slice_after() : 0;
+}
+
 static int default_slice_rounds() {
   static const int v = [] {
     const char* e = getenv("DIB_SLICE_ROUNDS");          // tuning knob; results depend on it at rounding level only
@@ -1746,7 +1821,7 @@ static int check_cloud_args(const CT* xyz, const int8_t* label, int n_stride, in
 
 // Optional CUDA events recorded right before / after the solve kernel on its launch stream (dib_profile_solve_events):
 // lets a benchmark time the dominant kernel INSIDE its timed steps instead of in a separate loop.
-static thread_local int g_eval_pass = 0;        // dib_evaluate_pass_index: which pass of a solve frustum_evaluate_* mimics
+static thread_local int g_eval_sliced = 1;      // dib_evaluate_sliced: frustum_evaluate_* forms its sums slice by slice (1) or in one piece (0)
 static thread_local void* g_ev_start = nullptr;
 static thread_local void* g_ev_stop = nullptr;
 
@@ -1783,6 +1858,7 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   // One CTA (a team of kW warps, one problem per warp) per SM.  A batch with fewer problems than warps is spread
   // one problem per CTA first (the kernel deals the first wave rank-major), so the spare warps of every CTA help.
   long long grid = (long long)cfg.sms * cfg.per_sm;
+  a.slice_after = slice_after_for(total, grid * kW);
   if (grid > total) grid = total;
   // scheduling chunk: the queue walks chunks of samples rank-major (longest-predicted inits of every sample of the
   // chunk first).  Larger chunks start the long solves earlier (shorter tail); smaller chunks keep the packed clouds
@@ -1810,7 +1886,7 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
 
 static size_t solve_workspace_bytes_impl(int S, int I, int n_stride) {
   const size_t n = (size_t)(S > 0 ? S : 0) * (size_t)(I > 0 ? I : 0);
-  return 256 + align_up(n * 6 * sizeof(double), 256) + align_up(n * sizeof(double), 256) +
+  return kHeaderBytes + align_up(n * 6 * sizeof(double), 256) + align_up(n * sizeof(double), 256) +
          align_up(n * 4 * sizeof(int32_t), 256) + box_table_bytes(S, n_stride > 0 ? n_stride : 0) +
          packed_bytes(S, n_stride > 0 ? n_stride : 0) + align_up(n * sizeof(int32_t), 256);
 }
@@ -1838,7 +1914,7 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   const size_t n = (size_t)S * I;
   SolveArgs a;
   a.queue = (unsigned int*)ws;
-  size_t off = 256;
+  size_t off = kHeaderBytes;
   a.params_all = params_all ? params_all : (double*)(ws + off);
   off += align_up(n * 6 * sizeof(double), 256);
   a.cost_all = cost_all ? cost_all : (double*)(ws + off);
@@ -1859,9 +1935,9 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   a.H = H; a.W = W; a.max_iter = max_iter; a.S = S; a.I = I;
   a.chunk = 1;
   a.slice_rounds = default_slice_rounds();
-  a.slice_after = default_slice_after();
+  a.slice_after = 0;                                   // decided in launch_solve (needs the grid)
   a.trace = trace; a.trace_cap = trace_cap;
-  DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, 256, st));
+  DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, kHeaderBytes, st));
   DIB_CHECK_CUDA(cudaMemsetAsync((unsigned char*)a.queue + 8, 0xff, 16, st));   // timeline minima start at ~0ull
   if (trace) DIB_CHECK_CUDA(cudaMemsetAsync(trace, 0, n * (size_t)trace_cap * kTraceRec * sizeof(double), st));
   rc = launch_boxes<CT>(xyz, label, n_pts, n_stride, S, table, packed, st);
@@ -1894,7 +1970,7 @@ static int launch_evaluate(const int32_t* n_pts, int n_stride, const double* K9,
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   kern<<<S, kEvalWarps * 32, smem, st>>>(n_pts, n_stride, K9, x, H, W, table, packed, box_rounds(n_stride),
-                                         default_slice_rounds(), g_eval_pass >= default_slice_after() ? 1 : 0, cost_out,
+                                         default_slice_rounds(), g_eval_sliced, cost_out,
                                          grad_out, JtJ_out);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
@@ -1946,7 +2022,19 @@ extern "C" {
 int dib_abi_version(void) { return 3; }
 const char* dib_last_error(void) { return dib::g_err; }
 
-void dib_evaluate_pass_index(int pass_index) { dib::g_eval_pass = pass_index < 0 ? 0 : pass_index; }
+void dib_evaluate_sliced(int on) { dib::g_eval_sliced = on ? 1 : 0; }
+
+int frustum_solve_slice_after(int S, int I, int is_2d, int f64_record) {
+  dib::LaunchCfg cfg;
+  int rc;
+  int kw;
+  if (f64_record) { rc = is_2d ? dib::solver_launch_cfg<double, 4>(&cfg) : dib::solver_launch_cfg<double, 6>(&cfg);
+                    kw = is_2d ? dib::Cfg<double, 4>::kWarps : dib::Cfg<double, 6>::kWarps; }
+  else { rc = is_2d ? dib::solver_launch_cfg<float, 4>(&cfg) : dib::solver_launch_cfg<float, 6>(&cfg);
+         kw = is_2d ? dib::Cfg<float, 4>::kWarps : dib::Cfg<float, 6>::kWarps; }
+  if (rc != DIB_OK) return rc;
+  return dib::slice_after_for((long long)S * I, (long long)cfg.sms * cfg.per_sm * kw);
+}
 
 void dib_profile_solve_events(void* start_event, void* stop_event) {
   dib::g_ev_start = start_event;

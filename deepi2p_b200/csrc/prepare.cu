@@ -52,17 +52,82 @@ __device__ __forceinline__ uint32_t spread6(uint32_t v) {   // 6 bits -> every o
   return v;
 }
 
+// One stable counting-sort pass over 7 bits of the 16-bit keys (all kPrepThreads threads call).  `in` = current order
+// of the point indices (NULL = identity), `out` = the order after this digit.  Warp w owns a contiguous range of the
+// input and walks it 32 elements at a time, so equal digits keep their input order (match_any gives the rank among the
+// lanes of a tile, the per-(warp, digit) cursor the rank among earlier tiles, the scan the rank among earlier warps).
+__device__ void radix_pass(const uint16_t* k16, const uint16_t* in, uint16_t* out, int n, int shift, uint32_t* hist,
+                           uint32_t* tot) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < kPrepWarps * 128; i += kPrepThreads) hist[i] = 0u;
+  __syncthreads();
+  const int R = ((((n + kPrepWarps - 1) / kPrepWarps) + 31) / 32) * 32;
+  const int lo = min(warp * R, n), hi = min(lo + R, n);
+  for (int j = lo + lane; j < hi; j += 32) {
+    const int src = in ? (int)in[j] : j;
+    atomicAdd(&hist[warp * 128 + ((k16[src] >> shift) & 127)], 1u);
+  }
+  __syncthreads();
+  if (tid < 128) {                                 // per digit: exclusive prefix over the warps, and the digit's total
+    uint32_t sum = 0;
+    for (int w = 0; w < kPrepWarps; ++w) { const uint32_t v = hist[w * 128 + tid]; hist[w * 128 + tid] = sum; sum += v; }
+    tot[tid] = sum;
+  }
+  __syncthreads();
+  if (tid < 32) {                                  // exclusive scan of the 128 totals (one warp, 4 digits per lane)
+    uint32_t v[4], run = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { v[q] = tot[4 * tid + q]; run += v[q]; }
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    uint32_t base = inc - run;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { tot[4 * tid + q] = base; base += v[q]; }
+  }
+  __syncthreads();
+  if (tid < 128) {
+    const uint32_t base = tot[tid];
+    for (int w = 0; w < kPrepWarps; ++w) hist[w * 128 + tid] += base;
+  }
+  __syncthreads();
+  const unsigned lt = (1u << lane) - 1u;
+  for (int j0 = lo; j0 < hi; j0 += 32) {
+    const int j = j0 + lane;
+    const bool valid = j < hi;
+    const int src = valid ? (in ? (int)in[j] : j) : 0;
+    const unsigned d = valid ? ((k16[src] >> shift) & 127u) : (128u + (unsigned)lane);     // invalid lanes match nobody
+    const unsigned m = __match_any_sync(0xffffffffu, d);
+    const int rank = __popc(m & lt);
+    uint32_t base = 0;
+    if (valid) base = hist[warp * 128 + d];
+    __syncwarp();
+    if (valid) {
+      out[base + rank] = (uint16_t)src;
+      if (rank == 0) hist[warp * 128 + d] = base + (uint32_t)__popc(m);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+}
+
 // grid = S.  xyz_in [S][3][n_in_stride] f32, pred [S][n_in_stride] int8, n_in points valid.
 // do_sort: order the kept points by (label class, 12-bit Morton cell of (x, z), original index) with an
-// in-shared-memory bitonic sort of 32-bit composite keys (needs n_in <= kSortMax and n2 * 4 bytes of
-// dynamic shared memory, n2 = next power of two >= n_in); otherwise the original order is kept.
+// in-shared-memory stable radix sort (needs n_in <= kSortMax and radix_smem_bytes(n2) of dynamic shared memory,
+// n2 = n_in rounded up to 8); otherwise the original order is kept.
 __global__ void __launch_bounds__(kPrepThreads)
     frustum_prepare_kernel(const float* __restrict__ xyz_in, const int8_t* __restrict__ pred, int n_in,
                            int n_in_stride, int n_out_stride, int I, unsigned long long seed, double ry_sigma,
                            double t_amp, int do_sort, int n2, float* __restrict__ xyz_out,
                            int8_t* __restrict__ label_out, int32_t* __restrict__ n_pts, double* __restrict__ init,
                            double* __restrict__ init_y_angle, int32_t* __restrict__ degenerate) {
-  extern __shared__ __align__(16) uint32_t keys[];
+  extern __shared__ __align__(16) unsigned char prep_smem[];
+  // sort scratch (do_sort only): per-warp digit histograms, bucket totals, 16-bit keys and two index arrays
+  uint32_t* hist = reinterpret_cast<uint32_t*>(prep_smem);                 // [kPrepWarps][128]
+  uint32_t* tot = hist + kPrepWarps * 128;                                 // [128]
+  uint16_t* k16 = reinterpret_cast<uint16_t*>(tot + 128);                  // [n2]
+  uint16_t* ord1 = k16 + n2;                                               // [n2]
+  uint16_t* ord2 = ord1 + n2;                                              // [n2]
   __shared__ double scratch[kPrepWarps];
   __shared__ float fscratch[kPrepWarps];
   __shared__ int iscratch[kPrepWarps];
@@ -123,38 +188,29 @@ __global__ void __launch_bounds__(kPrepThreads)
     zlo = block_reduce(zlo, fscratch, fmn); zhi = block_reduce(zhi, fscratch, fmx);
     n_front = block_reduce(kept, iscratch, isum);
     const float xs = (xhi > xlo) ? 64.0f / (xhi - xlo) : 0.0f, zs = (zhi > zlo) ? 64.0f / (zhi - zlo) : 0.0f;
-    // pass 3b: composite keys  [class:2 | morton:12 | index:15], dropped points and padding sort last
-    for (int i = tid; i < n2; i += kPrepThreads) {
-      uint32_t key = 0xFFFFFFFFu;
-      if (i < n_in) {
-        const float x = px[i], z = pz[i];
-        if (degen || (-sn * (double)x + cs * (double)z) > thresh) {
-          const int l = lab[i];
-          const uint32_t cls = (l == 0) ? 0u : (l == 1 ? 1u : 2u);
-          const uint32_t qx = (uint32_t)fminf(fmaxf((x - xlo) * xs, 0.0f), 63.0f);
-          const uint32_t qz = (uint32_t)fminf(fmaxf((z - zlo) * zs, 0.0f), 63.0f);
-          key = (cls << 27) | (((spread6(qx) << 1) | spread6(qz)) << 15) | (uint32_t)i;
-        }
+    // pass 3b: 14-bit sort keys  [class:2 | morton:12]  (dropped points: all ones, they sort last)
+    for (int i = tid; i < n_in; i += kPrepThreads) {
+      uint32_t key = 0x3FFFu;
+      const float x = px[i], z = pz[i];
+      if (degen || (-sn * (double)x + cs * (double)z) > thresh) {
+        const int l = lab[i];
+        const uint32_t cls = (l == 0) ? 0u : (l == 1 ? 1u : 2u);
+        const uint32_t qx = (uint32_t)fminf(fmaxf((x - xlo) * xs, 0.0f), 63.0f);
+        const uint32_t qz = (uint32_t)fminf(fmaxf((z - zlo) * zs, 0.0f), 63.0f);
+        key = (cls << 12) | (spread6(qx) << 1) | spread6(qz);
       }
-      keys[i] = key;
+      k16[i] = (uint16_t)key;
     }
     __syncthreads();
-    // pass 3c: bitonic sort (keys are unique -> deterministic)
-    for (int k = 2; k <= n2; k <<= 1) {
-      for (int j = k >> 1; j > 0; j >>= 1) {
-        for (int t = tid; t < (n2 >> 1); t += kPrepThreads) {
-          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-          const uint32_t a = keys[i], b = keys[i | j];
-          const bool up = (i & k) == 0;
-          if ((a > b) == up) { keys[i] = b; keys[i | j] = a; }
-        }
-        __syncthreads();
-      }
-    }
+    // pass 3c: STABLE least-significant-digit radix sort of the point indices by that key, two 7-bit digits.  Stable +
+    // ascending input order = ties broken by the original index, i.e. exactly the order of the unique composite key
+    // [class | morton | index]; O(n) per digit instead of the O(n log^2 n) bitonic network this replaces.
+    radix_pass(k16, nullptr, ord1, n_in, 0, hist, tot);
+    radix_pass(k16, ord1, ord2, n_in, 7, hist, tot);
     // pass 3d: gather in sorted order
     if (n_front > n_out_stride) n_front = n_out_stride;
     for (int i = tid; i < n_front; i += kPrepThreads) {
-      const int src = (int)(keys[i] & 0x7FFFu);
+      const int src = (int)ord2[i];
       const int8_t l = lab[src];
       ox[i] = px[src]; oy[i] = py[src]; oz[i] = pz[src];
       ol[i] = (l == 0 || l == 1) ? l : (int8_t)-1;
@@ -234,9 +290,8 @@ int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in,
   const int n_out_stride = (n_in + 15) & ~15;
   if (S == 0) return DIB_OK;
   const int do_sort = (sort != 0 && n_in <= kSortMax && n_in > 1) ? 1 : 0;
-  int n2 = 1;
-  while (n2 < n_in) n2 <<= 1;
-  const size_t smem = do_sort ? (size_t)n2 * sizeof(uint32_t) : 0;
+  const int n2 = (n_in + 7) & ~7;                  // array stride of the three 16-bit sort arrays
+  const size_t smem = do_sort ? (size_t)(kPrepWarps * 128 + 128) * sizeof(uint32_t) + (size_t)3 * n2 * sizeof(uint16_t) : 0;
   if (smem > 48 * 1024)
     DIB_CHECK_CUDA(cudaFuncSetAttribute(frustum_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   frustum_prepare_kernel<<<S, kPrepThreads, smem, (cudaStream_t)stream>>>(

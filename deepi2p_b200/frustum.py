@@ -142,6 +142,23 @@ def last_solve_timeline(device=None, stream=None, register_shape=None):
     return int(w[1]), int(w[2]), int(w[3])
 
 
+def last_solve_cta_end_times(device=None, stream=None, register_shape=None):
+    """Exit time (globaltimer ns) of every CTA of the most recent solve, zeros removed -- with last_solve_timeline this
+    shows whether the end-of-kernel tail is a few late SMs (imbalance) or all of them (critical path)."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), int(_stream_ptr(stream)))
+    buf = _ws_cache.get(key)
+    if buf is None:
+        return None
+    off = 0
+    if register_shape is not None:
+        lib = _native.load()
+        S, I, n_in = (int(v) for v in register_shape)
+        off = lib.frustum_register_workspace_bytes(S, I, n_in) - lib.frustum_solve_workspace_bytes(S, I, round_up(n_in, 16))
+    w = buf[off + 256:off + 256 + 8192].cpu().numpy().view(np.uint64)
+    return w[w > 0]
+
+
 def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB, max_iter=500,
                 is_2d=True, return_all=False, stream=None, out=None, trace_cap=0):
     """Batched multi-start solve, everything resident on the device.
@@ -212,12 +229,13 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
     return res
 
 
-def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None, pass_index=0):
-    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook).  pass_index: reproduce the sums of
-    that pass of a solve bit for bit (the solver cuts a pass into slices from its DIB_SLICE_AFTER-th pass on)."""
+def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None, sliced=True):
+    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook).  sliced: form the sums slice by
+    slice, as the solver does from a problem's slice_after-th pass on (frustum_solve_slice_after), or in one piece as
+    it does before; the two differ at rounding level, each reproduces the solver's own sums bit for bit."""
     _require_cuda()
     lib = _native.load()
-    lib.dib_evaluate_pass_index(int(pass_index))
+    lib.dib_evaluate_sliced(1 if sliced else 0)
     S, Ns = _check_cloud(xyz, label, n_pts)
     dev = xyz.device
     K9 = _as_K(K, S, dev)
@@ -238,20 +256,32 @@ def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None, pass_
     return cost, grad[:, :P], JtJ[:, :P * P].reshape(S, P, P)
 
 
-def residuals(xyz, label, n, K, x, H, W, is_2d=True, stream=None):
-    """Loss-corrected residual vector of one cloud at x (registration.cpp:150-155)."""
+def residuals(xyz, label, n, K, x, H, W, is_2d=True, stream=None, host_labels=None):
+    """Loss-corrected residual vector of one cloud at x (registration.cpp:150-155).  host_labels: the labels as a host
+    array if the caller still has them (the drop-in does) -- the row offsets are then a numpy prefix sum instead of four
+    small torch kernels and a device->host read."""
     _require_cuda()
     lib = _native.load()
     dev = xyz.device
     Ns = xyz.shape[-1]
-    lab = label.reshape(-1)[:n]
-    rows = torch.where(lab == 1, 3, torch.where(lab == 0, 1, 0)).to(torch.int32)
-    offs = (torch.cumsum(rows, 0, dtype=torch.int32) - rows).contiguous()
-    total = int(rows.sum().item())
+    if host_labels is not None:
+        hl = np.asarray(host_labels).reshape(-1)[:n]
+        rows = np.where(hl == 1, 3, np.where(hl == 0, 1, 0)).astype(np.int32)
+        offs_h = np.cumsum(rows, dtype=np.int64) - rows
+        total = int(rows.sum())
+        offs = torch.from_numpy(offs_h.astype(np.int32)).to(dev)
+    else:
+        lab = label.reshape(-1)[:n]
+        rows = torch.where(lab == 1, 3, torch.where(lab == 0, 1, 0)).to(torch.int32)
+        offs = (torch.cumsum(rows, 0, dtype=torch.int32) - rows).contiguous()
+        total = int(rows.sum().item())
     K9 = _as_K(K, 1, dev)
-    xx = torch.zeros(6, dtype=torch.float64, device=dev)
     xv = torch.as_tensor(x, dtype=torch.float64).reshape(-1)
-    xx[:xv.numel()] = xv.to(dev)
+    if xv.is_cuda and xv.numel() == 6:
+        xx = xv.contiguous()
+    else:
+        xx = torch.zeros(6, dtype=torch.float64, device=dev)
+        xx[:xv.numel()] = xv.to(dev)
     with torch.cuda.device(dev):
         res = torch.zeros((max(total, 1),), dtype=torch.float64, device=dev)
         fn = lib.frustum_residuals_f32 if xyz.dtype == torch.float32 else lib.frustum_residuals_f64
@@ -363,9 +393,9 @@ def solve_p_given_k(points, labels, K, init_y_angle, init_T, H, W, t_xyz_lower_b
     init = torch.tensor([[[float(init_y_angle), T[0], T[1], T[2]]]], dtype=torch.float64)
     out = solve_batch(xyz, l8, n_pts, np.asarray(K, dtype=np.float64), init, H, W, lb[:3], ub[:3], int(max_iter),
                       bool(is_2d), return_all=True)
-    P = 4 if is_2d else 6
-    x = out["params"][0, 0, :P]
-    res = residuals(xyz[0], l8[0], pts.shape[1], np.asarray(K, dtype=np.float64), x, H, W, bool(is_2d))
+    x = out["params"][0, 0]                  # all six slots (unused ones are zero): goes to the kernel without a copy
+    res = residuals(xyz[0], l8[0], pts.shape[1], np.asarray(K, dtype=np.float64), x, H, W, bool(is_2d),
+                    host_labels=lab)
     if is_debug:
         st = out["stats"][0, 0].tolist()
         print("deepi2p_b200 solvePGivenK: iterations=%d evaluations=%d line_search_steps=%d termination=%s cost=%.6e"

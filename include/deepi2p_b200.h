@@ -110,10 +110,13 @@ int frustum_solve_traced_f32(const float* xyz, const int8_t* label, const int32_
                              double* trace, int trace_cap,
                              void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
-/* frustum_evaluate_* reproduces, bit for bit, the sums the solver forms at pass number `pass_index` of a solve (the
- * solver evaluates a problem's first DIB_SLICE_AFTER passes as one slice and later ones as a fixed sequence of
- * slices; the two differ at rounding level).  Thread-local, default 0.  Parity tooling. */
-void dib_evaluate_pass_index(int pass_index);
+/* Slicing policy (parity tooling).  The solver forms the sums of a pass either in one piece or as a fixed sequence of
+ * slices added in slice order (so that idle warps can help); the two differ at rounding level.  A problem's passes are
+ * sliced from its frustum_solve_slice_after(S, I, ...)-th pass on: 0 for a batch smaller than ~4 waves of the machine,
+ * DIB_SLICE_AFTER (48) otherwise.  dib_evaluate_sliced (thread-local, default 1) selects which of the two
+ * frustum_evaluate_* reproduces bit for bit. */
+int frustum_solve_slice_after(int S, int I, int is_2d, int f64_record);
+void dib_evaluate_sliced(int on);
 
 /* One evaluation pass per sample at explicit parameters x [S][6] f64:
  * cost_out [S], grad_out [S][6] (J^T r), JtJ_out [S][36] (row-major P x P in the top-left).

@@ -20,7 +20,7 @@
 //     corrector.cc, loss_function.cc, line_search.cc, polynomial.cc, parameter_block.h.
 // Checked on the GPU box as well (profiles/r02_probe_ceres_gpu_box.txt): no Ceres, no Eigen there either.
 // Known deliberate deviation: roots of the degree-4 derivative polynomial in the 3-sample
-// line-search interpolation are found by Durand-Kerner iteration instead of companion
+// line-search interpolation are found by (total-step) Durand-Kerner iteration instead of companion
 // matrix eigenvalues (same roots, different rounding).
 //
 // Build: g++ -O2 -shared -fPIC -std=c++17 (see oracle/build.py).  C ABI at the bottom.
@@ -342,31 +342,46 @@ void poly_roots_real(std::vector<double> p, std::vector<double>* real) {
     } else { real->push_back(-b / (2.0 * a)); real->push_back(-b / (2.0 * a)); }
     return;
   }
-  typedef std::complex<double> cd;
-  std::vector<cd> z(deg);
+  // Durand-Kerner, total-step form (every root is updated from the previous iterate of all roots), written out in
+  // real arithmetic exactly as the CUDA kernel's warp-parallel version does it (one lane per root there).
+  double c[8], zr[8], zi[8], qr[8], qi[8];
+  for (int i = 0; i <= deg; ++i) c[i] = p[i] * (1.0 / p[0]);
   // Fujiwara's bound on the root moduli: 2 max_k |c_k|^(1/k) (the last coefficient halved)
   double radius = 0.0;
   for (int i = 1; i <= deg; ++i) {
-    const double a = std::fabs(p[i] / p[0]) * (i == deg ? 0.5 : 1.0);
+    const double a = std::fabs(c[i]) * (i == deg ? 0.5 : 1.0);
     radius = std::max(radius, a > 0.0 ? std::exp(std::log(a) / (double)i) : 0.0);
   }
   radius = 2.0 * radius + 1e-300;
-  for (int i = 0; i < deg; ++i) z[i] = std::polar(radius * 0.5, 2.0 * M_PI * i / deg + 0.4);
+  for (int i = 0; i < deg; ++i) {
+    const double ang = 2.0 * 3.14159265358979323846 * i / deg + 0.4;
+    zr[i] = 0.5 * radius * std::cos(ang); zi[i] = 0.5 * radius * std::sin(ang);
+  }
   for (int it = 0; it < 100; ++it) {
     double change = 0.0;
     for (int i = 0; i < deg; ++i) {
-      cd num(0.0, 0.0);
-      for (int k = 0; k <= deg; ++k) num = num * z[i] + cd(p[k] / p[0], 0.0);
-      cd den(1.0, 0.0);
-      for (int j = 0; j < deg; ++j) if (j != i) den *= (z[i] - z[j]);
-      if (std::abs(den) == 0.0) den = cd(1e-300, 0.0);
-      const cd dz = num / den;
-      z[i] -= dz;
-      change = std::max(change, std::abs(dz));
+      double nr = 0.0, ni = 0.0;
+      for (int k = 0; k <= deg; ++k) {
+        const double tr = nr * zr[i] - ni * zi[i] + c[k];
+        const double ti = nr * zi[i] + ni * zr[i];
+        nr = tr; ni = ti;
+      }
+      double dr = 1.0, di = 0.0;
+      for (int j = 0; j < deg; ++j) if (j != i) {
+        const double er = zr[i] - zr[j], ei = zi[i] - zi[j];
+        const double tr = dr * er - di * ei, ti = dr * ei + di * er;
+        dr = tr; di = ti;
+      }
+      double den = dr * dr + di * di;
+      if (den == 0.0) { dr = 1e-300; di = 0.0; den = dr * dr; if (den == 0.0) den = 1e-300; }
+      const double iden = 1.0 / den;
+      qr[i] = (nr * dr + ni * di) * iden; qi[i] = (ni * dr - nr * di) * iden;
+      change = std::max(change, std::sqrt(qr[i] * qr[i] + qi[i] * qi[i]));
     }
+    for (int i = 0; i < deg; ++i) { zr[i] -= qr[i]; zi[i] -= qi[i]; }
     if (change < 1e-14 * radius) break;
   }
-  for (int i = 0; i < deg; ++i) real->push_back(z[i].real());
+  for (int i = 0; i < deg; ++i) real->push_back(zr[i]);
 }
 
 // Minimise the polynomial interpolating the samples over [xmin, xmax].

@@ -78,9 +78,12 @@ def test_solve_matches_oracle(cuda, is_2d):
     solver stops on a 1e-6 relative function tolerance, so trajectories are chaotic at the rounding
     level: even the CPU oracle against itself with an algebraically equivalent linear solver moves
     ~3-4 % of full-size solves by > 1e-7 (tests/tools/parity_sensitivity_cpu.py).  The gate is therefore
-    statistical: at least 90 % of the (sample, init) solves within 1e-4 rad / 1e-3 m of the oracle
-    with identical iteration / evaluation counts, and a tiny median difference."""
-    S, I, n = 6, 5, 4096
+    statistical: at least 97 % of the (sample, init) solves within 1e-4 rad / 1e-3 m of the oracle, 93 % with
+    identical iteration / evaluation / termination records, a tiny median difference, and per registration either the
+    same best-of-I pose or a GPU best cost that is not worse than the oracle's.  (profiles/r02_trace_divergence.md
+    traces every out-of-gate solve of a 1440-solve full-size run to its first divergent evaluation and shows that
+    the same solves leave the gate when EITHER implementation's own input is moved by one ulp.)"""
+    S, I, n = 10, 12, 4096
     xs, ls, inits, Ks = [], [], [], []
     smps = []
     for s in range(S):
@@ -115,7 +118,8 @@ def test_solve_matches_oracle(cuda, is_2d):
                                and stats[s, i, 3] == ms["stats"][i]["termination"])
         # arg-min over inits and the 4x4 (only meaningful where the winning solve agreed)
         er, et = pose_err(out["P"][s].cpu().numpy(), ms["P"])
-        best_ok += int(er < ROT_TOL and et < TRANS_TOL and int(out["best"][s]) == ms["best"])
+        best_ok += int((er < ROT_TOL and et < TRANS_TOL and int(out["best"][s]) == ms["best"])
+                       or out["cost"][s].item() <= ms["cost"] * (1 + 1e-9))
         # the reported pose/cost are those of the reported best init
         b = int(out["best"][s])
         assert out["cost"][s].item() == costs[s, b] and b == int(np.argmin(costs[s]))
@@ -124,10 +128,10 @@ def test_solve_matches_oracle(cuda, is_2d):
     print("solves within gate %d/%d, identical counters %d/%d, best-of-I agree %d/%d, median rot %.2e trans %.2e, "
           "max rot %.2e trans %.2e" % (within.sum(), within.size, same_counts, within.size, best_ok, S,
                                        np.median(drs), np.median(dts), drs.max(), dts.max()))
-    assert within.mean() >= 0.9
-    assert same_counts >= 0.85 * within.size
+    assert within.mean() >= 0.97
+    assert same_counts >= 0.93 * within.size
     assert np.median(drs) < 1e-8 and np.median(dts) < 1e-7
-    assert best_ok >= S - 1
+    assert best_ok == S
 
 
 def test_known_answer_zero_cost_start(cuda):
@@ -327,6 +331,49 @@ def test_prepare_matches_initial_guess(cuda):
     np.testing.assert_array_equal(out["P"][4].cpu().numpy(), np.eye(4))
 
 
+def test_one_call_path_and_traces(cuda):
+    """(a) the ONE-call C entry (frustum_register_batch_f32) gives the bits of prepare + solve; (b) the traced solve
+    gives the bits of the plain solve, writes one record per cloud pass, and its records agree with the oracle's trace
+    (same evaluated points and decisions) on solves that end within the gate; (c) a second run reproduces the first
+    bit for bit (fixed-order sums, slice sums independent of which warp computed them)."""
+    S, I, n = 3, 5, 6000
+    smps = [small_sample(700 + s, n) for s in range(S)]
+    xyz_in, pred_in, _ = frustum.pack_clouds(np.stack([s["points"] for s in smps]), np.stack([s["pred"] for s in smps]))
+    K, H, W = smps[0]["K"], smps[0]["H"], smps[0]["W"]
+    reg = frustum.register_batch(xyz_in, pred_in, n, K, H, W, n_inits=I, seed=11, return_all=True)
+    prep = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=11)
+    assert torch.equal(prep["init"], reg["init"]) and torch.equal(prep["n_pts"], reg["n_pts"])
+    plain = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K, prep["init"], H, W, return_all=True)
+    traced = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K, prep["init"], H, W, return_all=True,
+                                 trace_cap=256)
+    again = frustum.register_batch(xyz_in, pred_in, n, K, H, W, n_inits=I, seed=11, return_all=True)
+    for key in ("P", "cost", "best", "params", "costs", "stats"):
+        assert torch.equal(reg[key], plain[key]), key
+        assert torch.equal(traced[key], plain[key]), key
+        assert torch.equal(again[key], reg[key]), key
+    tr = traced["trace"].cpu().numpy()
+    stats = plain["stats"].cpu().numpy()
+    params = plain["params"].cpu().numpy()
+    inits = prep["init"].cpu().numpy()
+    agree = total = 0
+    for s, smp in enumerate(smps):
+        _, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+        for i in range(I):
+            rec = tr[s, i][tr[s, i][:, 15] > 0]
+            assert len(rec) == stats[s, i, 1]                       # one record per cloud pass
+            assert rec[-1, 12] == stats[s, i, 3]                     # the last record carries the termination code
+            assert rec[0, 10] == 0 and np.array_equal(rec[0, :4], inits[s, i])
+            o = oracle.solve(pf, lf, K, inits[s, i, 0], inits[s, i, 1:4], H, W, syn.T_LB, syn.T_UB, 500, True,
+                             want_residuals=False, trace_cap=256)
+            if abs(params[s, i, 0] - o[4][0]) < ROT_TOL and np.linalg.norm(params[s, i, 1:4] - o[4][1:4]) < TRANS_TOL:
+                total += 1
+                to = o[5]
+                same = (len(to) == len(rec) and np.allclose(to[:, :4], rec[:, :4], rtol=0, atol=1e-6)
+                        and np.array_equal(to[:, 10:13], rec[:, 10:13]))
+                agree += int(same)
+    assert total >= S * I - 2 and agree >= total - 1
+
+
 def test_full_size_properties(cuda):
     """BASELINE-size cloud (20480 points): size-independent properties instead of the oracle --
     the returned cost equals a fresh evaluation at the returned pose, the cost never exceeds the
@@ -508,6 +555,6 @@ def test_committed_golden_vectors(cuda, is_2d):
     d_tr = np.linalg.norm(params[:, :, nr:P] - sol[:, :, nr:P], axis=2)
     within = (d_rot < ROT_TOL) & (d_tr < TRANS_TOL)
     print("golden solves within gate %d/%d" % (within.sum(), within.size))
-    assert within.sum() >= 0.75 * within.size
+    assert within.sum() >= within.size - 1        # the fixture's solves were picked stable under a 1e-13 input change
     costs = out["costs"].cpu().numpy()
     assert np.all(np.abs(costs[within] - sol[:, :, 6][within]) <= 1e-5 * np.maximum(1.0, sol[:, :, 6][within]))

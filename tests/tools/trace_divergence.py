@@ -75,7 +75,20 @@ def first_divergence(tg, to, P):
             kind = "smooth amplification (same decisions; the points drift apart across a kink of the objective)"
     seed_idx = max(0, min(e, n) - 1)
     lo = max(0, min(e, n) - 4)
+    # how the difference got there: the last evaluation at rounding level (< 1e-13), the first above 1e-10, and the
+    # geometric-mean growth per evaluation between the two (an expanding iteration amplifies rounding noise smoothly;
+    # a flipped decision shows up as a jump instead)
+    noise = np.nonzero(dx[:min(e, n) + 1] < 1e-13)[0]
+    last_noise = int(noise[-1]) if len(noise) else -1
+    above = np.nonzero(dx[:n] > 1e-10)[0]
+    first_above = int(above[0]) if len(above) else None
+    growth = None
+    if first_above is not None and last_noise >= 0 and first_above > last_noise and dx[last_noise] > 0:
+        growth = float((dx[first_above] / max(dx[last_noise], 1e-17)) ** (1.0 / (first_above - last_noise)))
+    first_flag = np.nonzero(~flags_equal)[0]
     return {
+        "last_evaluation_at_rounding_level": last_noise, "first_evaluation_above_1e-10": first_above,
+        "growth_per_evaluation": growth, "first_differing_decision": int(first_flag[0]) if len(first_flag) else None,
         "first_divergent_evaluation": e, "common_evaluations": n, "evaluations_gpu": len(tg), "evaluations_oracle": len(to),
         "kind": kind,
         "seed_before": {"evaluation": seed_idx, "max_rel_dx": float(dx[seed_idx]) if n else None,
@@ -185,6 +198,52 @@ def main():
         cost_le += int(g_costs[s, bg] <= oc[bo] * (1 + 1e-9))
         cost_rel.append(float(g_costs[s, bg] / oc[bo] - 1))
 
+    # ---- 2b. sensitivity of EACH implementation to its own input: the same solves with the init heading moved by ONE
+    # ulp.  A solve that leaves the gate under a 1-ulp change of its input cannot be expected to agree across two
+    # implementations that round differently.
+    inits_p = inits.copy()
+    inits_p[:, :, 0] = np.nextafter(inits_p[:, :, 0], np.inf)
+    g2 = frustum.solve_batch(prep["xyz"], prep["label"], prep["n_pts"], K, torch.from_numpy(inits_p).to(dev), H, W,
+                             max_iter=500, is_2d=is_2d, return_all=True)
+    g2_params = g2["params"].cpu().numpy().reshape(S * I, 6)
+
+    def run_oracle_perturbed():
+        def one(job):
+            s, i = job
+            pf, lf = per[s]
+            o = oracle.solve(pf, lf, K, inits_p[s, i, 0], inits_p[s, i, 1:4], H, W, syn.T_LB, syn.T_UB, 500, is_2d,
+                             want_residuals=False)
+            return o[4], o[1]
+        with ThreadPoolExecutor(threads) as ex:
+            r = list(ex.map(one, jobs))
+        return np.stack([x[0] for x in r]), np.array([x[1] for x in r])
+
+    qr_p2, qr_c2 = run_oracle_perturbed()
+    rep_gg, within_gg = compare(gp_flat, g2_params)
+    rep_oo, within_oo = compare(qr_p, qr_p2)
+    # registration level: does the best-of-I pose survive the 1-ulp change within each implementation?
+    def best_of(params_flat, costs_flat):
+        out = []
+        for s_ in range(S):
+            c_ = costs_flat[s_ * I:(s_ + 1) * I]
+            out.append(params_flat[s_ * I + int(np.argmin(c_))])
+        return np.stack(out)
+    g2_costs = g2["costs"].cpu().numpy().reshape(S * I)
+    o2_costs = None
+    unstable = ~(within_gg & within_oo)
+    qr_c = np.array([o[1] for o in o_qr])
+    bg, bg2 = best_of(gp_flat, g_costs.reshape(S * I)), best_of(g2_params, g2_costs)
+    bo, bo2 = best_of(qr_p, qr_c), best_of(qr_p2, qr_c2)
+    reg_gg = sum(int(param_diff(bg[s_], bg2[s_], P)[0] < ROT_TOL and param_diff(bg[s_], bg2[s_], P)[1] < TRANS_TOL) for s_ in range(S))
+    reg_oo = sum(int(param_diff(bo[s_], bo2[s_], P)[0] < ROT_TOL and param_diff(bo[s_], bo2[s_], P)[1] < TRANS_TOL) for s_ in range(S))
+    sens = {"gpu_vs_gpu_init_plus_1ulp": rep_gg, "oracle_vs_oracle_init_plus_1ulp": rep_oo,
+            "registrations_best_pose_unchanged_gpu": reg_gg, "registrations_best_pose_unchanged_oracle": reg_oo,
+            "solves_unstable_in_either": int(unstable.sum()),
+            "out_of_gate_gpu_vs_oracle": int((~within_gq).sum()),
+            "out_of_gate_that_are_unstable_under_1ulp": int((~within_gq & unstable).sum()),
+            "out_of_gate_but_stable_under_1ulp": [[args.first_id + jobs[k][0], jobs[k][1]] for k in range(len(jobs))
+                                                  if not within_gq[k] and not unstable[k]]}
+
     # ---- 3. first divergence of every out-of-gate solve (GPU vs oracle QR)
     def valid(tr):
         return tr[tr[:, 15] > 0]
@@ -201,14 +260,18 @@ def main():
                                                                      "termination_gpu": TERM[int(g_stats[s, i, 3])],
                                                                      "termination_oracle": TERM[o_qr[k][3]["termination"]]},
                   "also_out_of_gate_oracle_qr_vs_oracle_cholesky": bool(not within_qc[k]),
-                  "in_gate_gpu_vs_oracle_cholesky": bool(within_gc[k])})
+                  "in_gate_gpu_vs_oracle_cholesky": bool(within_gc[k]),
+                  "gpu_stable_under_1ulp_init_change": bool(within_gg[k]),
+                  "oracle_stable_under_1ulp_init_change": bool(within_oo[k])})
         out_of_gate.append(d)
 
     # ---- 4. hybrid: the oracle's control flow on the GPU kernel's sums (sorted cloud, same slices)
     hybrid_jobs = [k for k in range(len(jobs)) if not within_gq[k]]
     in_gate = [k for k in range(len(jobs)) if within_gq[k]]
     hybrid_jobs += in_gate[:: max(1, len(in_gate) // max(1, args.hybrid_in_gate))][:args.hybrid_in_gate]
-    hyb = {"solves": 0, "bit_identical_final_params": 0, "within_gate": 0, "identical_trace_points": 0, "rows": []}
+    from deepi2p_b200 import _native
+    slice_after = _native.load().frustum_solve_slice_after(S, I, 1 if is_2d else 0, 0)
+    hyb = {"slice_after_of_the_traced_solve": slice_after, "solves": 0, "bit_identical_final_params": 0, "within_gate": 0, "identical_trace_points": 0, "rows": []}
     for k in hybrid_jobs:
         s, i = jobs[k]
         pf, lf = per[s]
@@ -217,7 +280,7 @@ def main():
         calls = [0]
 
         def ext(x6, xs=xs, ls_=ls_, ns_=ns_, calls=calls):
-            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d, pass_index=calls[0])
+            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d, sliced=calls[0] >= slice_after)
             calls[0] += 1                 # the oracle evaluates in the same order as the kernel counts its passes
             return float(c[0]), gr[0].cpu().numpy(), A[0].cpu().numpy()
 
@@ -254,6 +317,7 @@ def main():
         "registrations": {"count": S, "best_of_I_pose_within_gate": reg_ok, "gpu_best_cost_le_oracle_best_cost": cost_le,
                           "best_cost_relative_difference": {"min": float(np.min(cost_rel)), "median": float(np.median(cost_rel)),
                                                             "max": float(np.max(cost_rel))}},
+        "one_ulp_sensitivity": sens,
         "hybrid_oracle_control_on_gpu_sums_vs_gpu": hyb,
         "out_of_gate_kinds": kinds,
         "out_of_gate_seed_rel_dx": ({"min": float(np.min(seeds)), "median": float(np.median(seeds)), "max": float(np.max(seeds))}
@@ -277,14 +341,24 @@ def main():
                 "QR oracle), bit-identical final parameters %d, identical evaluated points %d, within gate %d\n" % (
                     hyb["solves"], hyb["of_which_out_of_gate_vs_oracle_qr"], hyb["bit_identical_final_params"],
                     hyb["identical_trace_points"], hyb["within_gate"]))
-        f.write("\n## Every out-of-gate solve (GPU vs oracle QR): where the traces part\n\n")
-        f.write("| sample | init | first divergent eval | of (gpu/oracle) | seed rel dx before | rel dx at | kind | also QR-vs-Cholesky (CPU only) | final rot / trans |\n"
-                "|---|---|---|---|---|---|---|---|---|\n")
+        f.write("\n1-ulp sensitivity (init heading moved by one ulp, each implementation against ITSELF): GPU %d / %d within "
+                "gate, oracle %d / %d; %d of the %d solves that are out of gate GPU-vs-oracle are unstable under that 1-ulp "
+                "change in at least one implementation\n" % (
+                    rep_gg["within_gate"], rep_gg["solves"], rep_oo["within_gate"], rep_oo["solves"],
+                    sens["out_of_gate_that_are_unstable_under_1ulp"], sens["out_of_gate_gpu_vs_oracle"]))
+        f.write("\nregistration level under the same 1-ulp change: best-of-%d pose unchanged (within gate) for %d / %d registrations on "
+                "the GPU and %d / %d in the oracle\n" % (I, reg_gg, S, reg_oo, S))
+        f.write("\n## Every out-of-gate solve (GPU vs oracle QR): where the traces part\n\n"
+                "rel dx = max over parameters of |x_gpu - x_oracle| / (1 + |x|) at the same evaluation index.\n\n")
+        f.write("| sample | init | evals gpu/oracle | last eval at rounding level (<1e-13) | first eval > 1e-10 | growth / eval | "
+                "first eval > 1e-7 | first differing decision | kind | GPU stable under 1 ulp | oracle stable under 1 ulp | "
+                "QR-vs-Cholesky (CPU) out of gate | final rot / trans |\n|---|---|---|---|---|---|---|---|---|---|---|---|---|\n")
         for d in out_of_gate:
-            at = d["at_divergence"]
-            f.write("| %d | %d | %d | %d/%d | %.1e | %s | %s | %s | %.1e / %.1e |\n" % (
-                d["sample"], d["init"], d["first_divergent_evaluation"], d["evaluations_gpu"], d["evaluations_oracle"],
-                d["seed_before"]["max_rel_dx"] or 0.0, ("%.1e" % at["max_rel_dx"]) if at else "-", d["kind"],
+            f.write("| %d | %d | %d/%d | %s | %s | %s | %d | %s | %s | %s | %s | %s | %.1e / %.1e |\n" % (
+                d["sample"], d["init"], d["evaluations_gpu"], d["evaluations_oracle"], d["last_evaluation_at_rounding_level"],
+                d["first_evaluation_above_1e-10"], ("x%.1f" % d["growth_per_evaluation"]) if d["growth_per_evaluation"] else "-",
+                d["first_divergent_evaluation"], d["first_differing_decision"], d["kind"].split("(")[0].strip(),
+                d["gpu_stable_under_1ulp_init_change"], d["oracle_stable_under_1ulp_init_change"],
                 d["also_out_of_gate_oracle_qr_vs_oracle_cholesky"], d["final"]["rot_rad"], d["final"]["trans_m"]))
     print(json.dumps({k: v for k, v in report.items() if k != "out_of_gate"}))
 
