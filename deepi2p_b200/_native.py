@@ -11,7 +11,7 @@ _c = ctypes
 _lib = None
 
 EXPORTS = (
-    "dib_abi_version", "dib_last_error", "dib_device_sm_count", "dib_profile_solve_events", "dib_evaluate_sliced", "frustum_solve_slice_after",
+    "dib_abi_version", "dib_last_error", "dib_device_sm_count", "dib_profile_solve_events", "dib_evaluate_sliced", "frustum_solve_slice_after", "frustum_solve_slice_rounds",
     "frustum_solve_workspace_bytes", "frustum_solve_batch_f32", "frustum_solve_batch_f64", "frustum_solve_traced_f32",
     "frustum_register_workspace_bytes", "frustum_register_batch_f32",
     "frustum_evaluate_workspace_bytes",
@@ -69,6 +69,8 @@ def load():
     lib.dib_evaluate_sliced.argtypes = [i32]
     lib.frustum_solve_slice_after.restype = i32
     lib.frustum_solve_slice_after.argtypes = [i32, i32, i32, i32]
+    lib.frustum_solve_slice_rounds.restype = i32
+    lib.frustum_solve_slice_rounds.argtypes = [i32, i32, i32, i32]
     lib.dib_profile_solve_events.restype = None
     lib.dib_profile_solve_events.argtypes = [vp, vp]
     lib.frustum_solve_workspace_bytes.restype = sz

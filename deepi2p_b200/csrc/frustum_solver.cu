@@ -500,6 +500,9 @@ constexpr int kBoxRoundFloats = kBoxFields * kRoundGroups;
 #ifndef DIB_GPS
 #define DIB_GPS 2                             // undecided groups fetched + classified per step
 #endif
+#ifndef DIB_GROUP_PIPE
+#define DIB_GROUP_PIPE 0                      // 1: the loads of the next step's groups are issued before this step's are used
+#endif
 #ifndef DIB_SLICE_ROUNDS
 #define DIB_SLICE_ROUNDS 4                    // rounds (of 1024 points) per slice: 20480 points = 20 rounds = 5 slices
 #endif
@@ -732,26 +735,47 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
     // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
     // (independent instruction streams) and appended.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
 #pragma unroll 1
-    do {
-      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-      int glab[DIB_GPS];
-      // surely-active groups first (a step made only of them skips the classification), then the undecided ones
-      const bool have = (mask | mask_sure) != 0;
-      bool all_sure = true;
-      if (have) {
+    // take the next DIB_GPS groups (surely-active ones first: a step made only of them skips the classification,
+    // then the undecided ones) and issue their loads
+    auto take_groups = [&](CT* lx, CT* ly, CT* lz, int* ll, bool& sure_only) -> bool {
+      const bool any = (mask | mask_sure) != 0;
+      sure_only = true;
+      if (any) {
 #pragma unroll
         for (int u = 0; u < DIB_GPS; ++u) {
-          glab[u] = -1; gx[u] = 0; gy[u] = 0; gz[u] = 0;
+          ll[u] = -1; lx[u] = 0; ly[u] = 0; lz[u] = 0;
           if (mask | mask_sure) {
             const bool from_sure = mask_sure != 0;
             const int b = __ffs(from_sure ? mask_sure : mask) - 1;
             if (from_sure) mask_sure &= mask_sure - 1; else mask &= mask - 1;
-            all_sure = all_sure && from_sure;
+            sure_only = sure_only && from_sure;
             const Entry<CT> e = pk_s[(size_t)(r * kRoundGroups + b) * 32 + lane];      // this lane's point
-            glab[u] = (int)e.lab; gx[u] = e.x; gy[u] = e.y; gz[u] = e.z;
+            ll[u] = (int)e.lab; lx[u] = e.x; ly[u] = e.y; lz[u] = e.z;
           }
         }
       }
+      return any;
+    };
+#if DIB_GROUP_PIPE
+    // register software pipeline: the loads of the NEXT step are in flight while this step is drained / classified
+    CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+    int glab[DIB_GPS];
+    bool all_sure = true;
+    bool have = take_groups(gx, gy, gz, glab, all_sure);
+#endif
+#pragma unroll 1
+    do {
+#if DIB_GROUP_PIPE
+      CT nx[DIB_GPS], ny[DIB_GPS], nz[DIB_GPS];
+      int nlab[DIB_GPS];
+      bool nsure = true;
+      const bool nhave = take_groups(nx, ny, nz, nlab, nsure);
+#else
+      CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
+      int glab[DIB_GPS];
+      bool all_sure = true;
+      const bool have = take_groups(gx, gy, gz, glab, all_sure);
+#endif
 #pragma unroll 1
       while (pend0 >= threshold) {
         __syncwarp();
@@ -804,7 +828,17 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
           pend1 += __popc(m1);
         }
       }
+#if DIB_GROUP_PIPE
+      have = nhave;
+      all_sure = nsure;
+      if (nhave) {
+#pragma unroll
+        for (int u = 0; u < DIB_GPS; ++u) { gx[u] = nx[u]; gy[u] = ny[u]; gz[u] = nz[u]; glab[u] = nlab[u]; }
+      }
+    } while (have);
+#else
     } while (mask | mask_sure);
+#endif
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
@@ -1788,6 +1822,14 @@ static int slice_after_for(long long total_problems, long long resident_warps) {
   return total_problems >= 4 * resident_warps ? default_slice_after() : 0;
 }
 
+static int default_slice_rounds();
+// Rounds (of 1024 points) per slice.  A small batch (slice_after == 0: idle warps from the start) uses short slices so
+// that up to 10 warps can work on one pass of a 20480-point cloud; a large one the default length (fewer slice ends).
+static int slice_rounds_for(int slice_after) {
+  if (getenv("DIB_SLICE_ROUNDS")) return default_slice_rounds();
+  return slice_after == 0 ? 2 : default_slice_rounds();
+}
+
 static int default_slice_rounds() {
   static const int v = [] {
     const char* e = getenv("DIB_SLICE_ROUNDS");          // tuning knob; results depend on it at rounding level only
@@ -1821,7 +1863,7 @@ static int check_cloud_args(const CT* xyz, const int8_t* label, int n_stride, in
 
 // Optional CUDA events recorded right before / after the solve kernel on its launch stream (dib_profile_solve_events):
 // lets a benchmark time the dominant kernel INSIDE its timed steps instead of in a separate loop.
-static thread_local int g_eval_sliced = 1;      // dib_evaluate_sliced: frustum_evaluate_* forms its sums slice by slice (1) or in one piece (0)
+static thread_local int g_eval_slice_rounds = DIB_SLICE_ROUNDS;   // dib_evaluate_sliced: rounds per slice of frustum_evaluate_* (0 = one piece)
 static thread_local void* g_ev_start = nullptr;
 static thread_local void* g_ev_stop = nullptr;
 
@@ -1859,6 +1901,7 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   // one problem per CTA first (the kernel deals the first wave rank-major), so the spare warps of every CTA help.
   long long grid = (long long)cfg.sms * cfg.per_sm;
   a.slice_after = slice_after_for(total, grid * kW);
+  a.slice_rounds = slice_rounds_for(a.slice_after);
   if (grid > total) grid = total;
   // scheduling chunk: the queue walks chunks of samples rank-major (longest-predicted inits of every sample of the
   // chunk first).  Larger chunks start the long solves earlier (shorter tail); smaller chunks keep the packed clouds
@@ -1970,7 +2013,7 @@ static int launch_evaluate(const int32_t* n_pts, int n_stride, const double* K9,
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   kern<<<S, kEvalWarps * 32, smem, st>>>(n_pts, n_stride, K9, x, H, W, table, packed, box_rounds(n_stride),
-                                         default_slice_rounds(), g_eval_sliced, cost_out,
+                                         g_eval_slice_rounds > 0 ? g_eval_slice_rounds : 1, g_eval_slice_rounds > 0 ? 1 : 0, cost_out,
                                          grad_out, JtJ_out);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
@@ -2022,7 +2065,7 @@ extern "C" {
 int dib_abi_version(void) { return 3; }
 const char* dib_last_error(void) { return dib::g_err; }
 
-void dib_evaluate_sliced(int on) { dib::g_eval_sliced = on ? 1 : 0; }
+void dib_evaluate_sliced(int rounds_per_slice) { dib::g_eval_slice_rounds = rounds_per_slice < 0 ? 0 : rounds_per_slice; }
 
 int frustum_solve_slice_after(int S, int I, int is_2d, int f64_record) {
   dib::LaunchCfg cfg;
@@ -2034,6 +2077,11 @@ int frustum_solve_slice_after(int S, int I, int is_2d, int f64_record) {
          kw = is_2d ? dib::Cfg<float, 4>::kWarps : dib::Cfg<float, 6>::kWarps; }
   if (rc != DIB_OK) return rc;
   return dib::slice_after_for((long long)S * I, (long long)cfg.sms * cfg.per_sm * kw);
+}
+
+int frustum_solve_slice_rounds(int S, int I, int is_2d, int f64_record) {
+  const int after = frustum_solve_slice_after(S, I, is_2d, f64_record);
+  return after < 0 ? after : dib::slice_rounds_for(after);
 }
 
 void dib_profile_solve_events(void* start_event, void* stop_event) {

@@ -135,184 +135,6 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
   }
 }
 
-// ------------------------------------------------------------------------------------------
-// index_max, sorted-gather variant (the default when the row and the tables fit in shared memory).
-//
-// The streaming kernel above is bound by instruction issue, not by HBM: ~3 % of the elements beat the lagging
-// thresholds, and since any of the 32 lanes of a warp may be the one, most warp-steps take the divergent exact-update
-// path (22 instructions per element, ncu).  This variant has no data-dependent branch per element:
-//   * the cluster ids index[b, :] are shared by all C channels of a batch item, so the CTA sorts the positions
-//     0..N-1 of its current batch item ONCE by cluster id (stable counting sort in shared memory: per-warp
-//     histograms, match_any ranks) -- perm[] lists the points segment after segment, in ascending n inside a segment;
-//   * every data row (b, c) is streamed into shared memory by the TMA engine (one 4N-byte cp.async.bulk per row,
-//     double-buffered: row r+1 loads while row r is scanned; SASS UBLKCP + SYNCS);
-//   * each thread owns a contiguous run of sorted positions and scans it with a running (max, argmax) -- one 16-bit
-//     perm load, one gathered float load, one compare and two selects per element, strict `>` in ascending n, so the
-//     lowest n wins ties, NaN and values <= -1000 never win; at a segment border (at most ~2 per thread) the run's
-//     winner goes to the segment's 64-bit key (value bits << 32 | ~n) with atomicMax -- a total order, so the result is
-//     deterministic and equal to the reference's scan.
-// A persistent grid (one CTA per SM) walks contiguous ranges of the B*C rows, so a CTA re-sorts only when b changes.
-// ------------------------------------------------------------------------------------------
-constexpr int kIsThreads = 512;
-constexpr int kIsWarps = kIsThreads / 32;
-
-struct IsLayout {
-  int E, stride;                       // sorted positions per thread; its perm slice in 16-bit entries (odd word count)
-  size_t row[2], perm, hist, seg, best[2], total;
-};
-__host__ __device__ inline IsLayout is_layout(int N, int K) {
-  IsLayout L;
-  L.E = (N + kIsThreads - 1) / kIsThreads;
-  if (L.E & 1) ++L.E;
-  int words = L.E / 2;
-  if ((words & 1) == 0) ++words;       // odd stride in 32-bit words: the 32 lanes' perm reads hit 32 different banks
-  L.stride = words * 2;
-  size_t o = 0;
-  auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 15) & ~(size_t)15; return at; };
-  L.row[0] = take((size_t)N * 4); L.row[1] = take((size_t)N * 4);
-  L.perm = take((size_t)kIsThreads * L.stride * 2);
-  L.hist = take((size_t)kIsWarps * (K + 1) * 4);
-  L.seg = take((size_t)(K + 2) * 4);
-  L.best[0] = take((size_t)K * 8); L.best[1] = take((size_t)K * 8);
-  L.total = o;
-  return L;
-}
-
-__global__ void __launch_bounds__(kIsThreads, 1) index_max_sorted_kernel(const float* __restrict__ data,
-                                                                        const int32_t* __restrict__ index,
-                                                                        int32_t* __restrict__ out, int B, int C, int N,
-                                                                        int K) {
-  extern __shared__ __align__(16) unsigned char is_smem[];
-  __shared__ __align__(8) uint64_t full[2];
-  const IsLayout L = is_layout(N, K);
-  float* rowbuf[2] = {reinterpret_cast<float*>(is_smem + L.row[0]), reinterpret_cast<float*>(is_smem + L.row[1])};
-  uint16_t* perm = reinterpret_cast<uint16_t*>(is_smem + L.perm);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(is_smem + L.hist);              // [kIsWarps][K + 1]
-  uint32_t* seg = reinterpret_cast<uint32_t*>(is_smem + L.seg);                // start of segment k; seg[K] = end of the valid ones
-  unsigned long long* best[2] = {reinterpret_cast<unsigned long long*>(is_smem + L.best[0]),
-                                 reinterpret_cast<unsigned long long*>(is_smem + L.best[1])};
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long rows = (long long)B * C;
-  const long long r0 = rows * blockIdx.x / gridDim.x, r1 = rows * (blockIdx.x + 1) / gridDim.x;
-  if (r0 >= r1) return;
-  const uint32_t row_bytes = (uint32_t)N * 4u;
-  if (tid == 0) {
-    mbar_init(&full[0], 1); mbar_init(&full[1], 1);
-    mbar_fence_init();
-    for (int q = 0; q < 2 && r0 + q < r1; ++q) {
-      mbar_expect_tx(&full[q], row_bytes);
-      bulk_g2s(rowbuf[q], data + (size_t)(r0 + q) * N, row_bytes, &full[q]);
-    }
-  }
-  for (int i = tid; i < 2 * K; i += kIsThreads) (i < K ? best[0][i] : best[1][i - K]) = 0ull;
-  __syncthreads();
-
-  const int E = L.E, stride = L.stride;
-  const int KB = K + 1;                               // bucket K collects out-of-range ids (undefined in the reference; skipped)
-  int cur_b = -1, p0 = 0, p1 = 0, k0 = 0;
-  const unsigned lt = (1u << lane) - 1u;
-  for (long long r = r0; r < r1; ++r) {
-    const int b = (int)(r / C);
-    const int buf = (int)((r - r0) & 1);
-    if (b != cur_b) {
-      // ---- stable counting sort of the positions of batch item b by cluster id
-      cur_b = b;
-      const int32_t* idx = index + (size_t)b * N;
-      for (int i = tid; i < kIsWarps * KB; i += kIsThreads) hist[i] = 0u;
-      __syncthreads();
-      const int R = ((((N + kIsWarps - 1) / kIsWarps) + 31) / 32) * 32;
-      const int lo = min(warp * R, N), hi = min(lo + R, N);
-      for (int j = lo + lane; j < hi; j += 32) {
-        const int k = __ldg(idx + j);
-        atomicAdd(&hist[warp * KB + ((unsigned)k < (unsigned)K ? k : K)], 1u);
-      }
-      __syncthreads();
-      for (int d = tid; d < KB; d += kIsThreads) {
-        uint32_t sum = 0;
-        for (int w = 0; w < kIsWarps; ++w) { const uint32_t v = hist[w * KB + d]; hist[w * KB + d] = sum; sum += v; }
-        seg[d] = sum;
-      }
-      __syncthreads();
-      if (warp == 0) {                                // exclusive scan of the KB bucket totals
-        const int chunk = (KB + 31) / 32;
-        uint32_t run = 0;
-        for (int q = 0; q < chunk; ++q) { const int d = lane * chunk + q; if (d < KB) run += seg[d]; }
-        uint32_t inc = run;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-        uint32_t base = inc - run;
-        for (int q = 0; q < chunk; ++q) {
-          const int d = lane * chunk + q;
-          if (d < KB) { const uint32_t v = seg[d]; seg[d] = base; base += v; }
-        }
-        if (lane == 31) seg[KB] = (uint32_t)N;
-      }
-      __syncthreads();
-      for (int d = tid; d < KB; d += kIsThreads) {
-        const uint32_t base = seg[d];
-        for (int w = 0; w < kIsWarps; ++w) hist[w * KB + d] += base;
-      }
-      __syncthreads();
-      for (int j0 = lo; j0 < hi; j0 += 32) {
-        const int j = j0 + lane;
-        const bool valid = j < hi;
-        const int k = valid ? __ldg(idx + j) : 0;
-        const unsigned d = valid ? ((unsigned)k < (unsigned)K ? (unsigned)k : (unsigned)K) : (0x10000u + (unsigned)lane);
-        const unsigned m = __match_any_sync(0xffffffffu, d);
-        const int rank = __popc(m & lt);
-        uint32_t base = 0;
-        if (valid) base = hist[warp * KB + d];
-        __syncwarp();
-        if (valid) {
-          const uint32_t pos = base + (uint32_t)rank;
-          perm[(pos / (uint32_t)E) * (uint32_t)stride + (pos % (uint32_t)E)] = (uint16_t)j;
-          if (rank == 0) hist[warp * KB + d] = base + (uint32_t)__popc(m);
-        }
-        __syncwarp();
-      }
-      __syncthreads();
-      // this thread's run of sorted positions and the segment it starts in
-      const int nvalid = (int)seg[K];
-      p0 = min(tid * E, nvalid);
-      p1 = min(p0 + E, nvalid);
-      int a = 0, z = K;                               // first k with seg[k + 1] > p0
-      while (a < z) { const int mid = (a + z) >> 1; if ((int)seg[mid + 1] > p0) z = mid; else a = mid + 1; }
-      k0 = a;
-    }
-    mbar_wait(&full[buf], (uint32_t)((r - r0) >> 1) & 1u);
-    {
-      const float* row = rowbuf[buf];
-      int p = p0, k = k0;
-      const uint16_t* pp = perm + (size_t)tid * stride;
-      while (p < p1) {
-        const int run_end = min((int)seg[k + 1], p1);
-        float bv = -1000.0f;
-        int bn = -1;
-#pragma unroll 4
-        for (; p < run_end; ++p) {
-          const int n = pp[p - p0];
-          const float v = row[n];
-          if (v > bv) { bv = v; bn = n; }
-        }
-        if (bn >= 0) atomicMax(&best[buf][k], ((unsigned long long)ordered_bits(bv) << 32) | (unsigned long long)(0xFFFFFFFFu - (uint32_t)bn));
-        ++k;
-        while (k < K && (int)seg[k + 1] <= p) ++k;    // skip empty segments
-      }
-    }
-    __syncthreads();                                  // the row is scanned: its buffer can be refilled, its winners are final
-    if (tid == 0 && r + 2 < r1) {
-      fence_proxy_async();
-      mbar_expect_tx(&full[buf], row_bytes);
-      bulk_g2s(rowbuf[buf], data + (size_t)(r + 2) * N, row_bytes, &full[buf]);
-    }
-    for (int t = tid; t < K; t += kIsThreads) {
-      const unsigned long long key = best[buf][t];
-      out[(size_t)r * K + t] = key ? (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)) : 0;
-      best[buf][t] = 0ull;                            // next used two rows later, behind the next row's barrier
-    }
-  }
-}
-
 constexpr int kBqWarps = 8;
 constexpr int kBqUnroll = 32;       // 4 KB per warp in flight
 
@@ -428,29 +250,6 @@ int index_max_forward(const float* data, const int32_t* index, int32_t* out, int
   DIB_REQUIRE(B <= 65535, "B too large for grid.y");
   if (B == 0 || C == 0) return DIB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static const bool force_streaming = getenv("DIB_INDEX_MAX_STREAMING") != nullptr;      // tuning / A-B knob
-  if (N % 4 == 0 && N >= 4 && N <= 65536 && ((uintptr_t)data % 16 == 0) && K <= 4096 && !force_streaming) {
-    const dib::IsLayout L = dib::is_layout(N, K);
-    if (L.total <= 226 * 1024) {
-      static int sms_cache[64] = {};
-      int dev = 0;
-      DIB_CHECK_CUDA(cudaGetDevice(&dev));
-      if (dev < 0 || dev >= 64 || sms_cache[dev] == 0) {
-        int sms = 0;
-        DIB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        DIB_CHECK_CUDA(cudaFuncSetAttribute(dib::index_max_sorted_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            226 * 1024));
-        if (dev >= 0 && dev < 64) sms_cache[dev] = sms;
-        else sms_cache[0] = sms;
-      }
-      const int sms = (dev >= 0 && dev < 64) ? sms_cache[dev] : sms_cache[0];
-      const long long rows = (long long)B * C;
-      const int grid = (int)(rows < sms ? rows : sms);
-      dib::index_max_sorted_kernel<<<grid, dib::kIsThreads, L.total, st>>>(data, index, out, B, C, N, K);
-      DIB_CHECK_CUDA(cudaGetLastError());
-      return DIB_OK;
-    }
-  }
   const bool vec = (N % 4 == 0) && ((uintptr_t)data % 16 == 0) && ((uintptr_t)index % 16 == 0);
   const size_t per_c = (size_t)K * 12;
   const size_t limit = 227 * 1024;

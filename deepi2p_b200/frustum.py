@@ -229,13 +229,14 @@ def solve_batch(xyz, label, n_pts, K, init, H, W, t_lb=DEFAULT_T_LB, t_ub=DEFAUL
     return res
 
 
-def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None, sliced=True):
-    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook).  sliced: form the sums slice by
-    slice, as the solver does from a problem's slice_after-th pass on (frustum_solve_slice_after), or in one piece as
-    it does before; the two differ at rounding level, each reproduces the solver's own sums bit for bit."""
+def evaluate_batch(xyz, label, n_pts, K, x, H, W, is_2d=True, stream=None, slice_rounds=4):
+    """One cost / gradient / J^T J pass per sample at parameters x [S,6] (test hook).  slice_rounds: form the sums in
+    slices of that many rounds of 1024 points (0 = in one piece) -- the solver uses frustum_solve_slice_rounds() from a
+    problem's frustum_solve_slice_after()-th pass on and one piece before; the variants differ at rounding level, each
+    reproduces the solver's own sums bit for bit."""
     _require_cuda()
     lib = _native.load()
-    lib.dib_evaluate_sliced(1 if sliced else 0)
+    lib.dib_evaluate_sliced(int(slice_rounds))
     S, Ns = _check_cloud(xyz, label, n_pts)
     dev = xyz.device
     K9 = _as_K(K, S, dev)

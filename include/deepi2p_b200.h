@@ -111,12 +111,14 @@ int frustum_solve_traced_f32(const float* xyz, const int8_t* label, const int32_
                              void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
 /* Slicing policy (parity tooling).  The solver forms the sums of a pass either in one piece or as a fixed sequence of
- * slices added in slice order (so that idle warps can help); the two differ at rounding level.  A problem's passes are
- * sliced from its frustum_solve_slice_after(S, I, ...)-th pass on: 0 for a batch smaller than ~4 waves of the machine,
- * DIB_SLICE_AFTER (48) otherwise.  dib_evaluate_sliced (thread-local, default 1) selects which of the two
- * frustum_evaluate_* reproduces bit for bit. */
+ * slices (frustum_solve_slice_rounds x 1024 points each) added in slice order, so that idle warps can help; the
+ * variants differ at rounding level, each is deterministic.  A batch of fewer than ~4 waves of problems slices every
+ * pass into short slices (slice_after 0, 2 rounds); a larger one slices only from a problem's 48th pass on, 4 rounds
+ * per slice.  dib_evaluate_sliced(r) (thread-local; r = rounds per slice, 0 = one piece; default 4) selects which of
+ * them frustum_evaluate_* reproduces bit for bit. */
 int frustum_solve_slice_after(int S, int I, int is_2d, int f64_record);
-void dib_evaluate_sliced(int on);
+int frustum_solve_slice_rounds(int S, int I, int is_2d, int f64_record);
+void dib_evaluate_sliced(int rounds_per_slice);
 
 /* One evaluation pass per sample at explicit parameters x [S][6] f64:
  * cost_out [S], grad_out [S][6] (J^T r), JtJ_out [S][36] (row-major P x P in the top-left).

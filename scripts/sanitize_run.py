@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepi2p_b200 import frustum, point_ops, synthetic as syn
 
 which = sys.argv[1] if len(sys.argv) > 1 else "all"
-S, n, I = 2, 1500, 3
+S, n, I = 2, 6000, 3        # 6 rounds of 1024 points = 2 slices per pass: the 6 problems run on 6 CTAs whose other warps HELP
 smps = [syn.make_sample(40 + s, n) for s in range(S)]
 xyz_in, pred_in, _ = frustum.pack_clouds(np.stack([s["points"] for s in smps]), np.stack([s["pred"] for s in smps]))
 if which in ("all", "solver"):
@@ -13,6 +13,10 @@ if which in ("all", "solver"):
         out = frustum.register_batch(xyz_in, pred_in, n, smps[0]["K"], smps[0]["H"], smps[0]["W"], n_inits=I, seed=3,
                                      is_2d=is_2d, return_all=True)
         print("register_batch", is_2d, out["cost"].cpu().numpy())
+    tr = frustum.solve_batch(*[frustum.prepare_batch(xyz_in, pred_in, n, I, seed=3)[k] for k in ("xyz", "label", "n_pts")],
+                             smps[0]["K"], frustum.prepare_batch(xyz_in, pred_in, n, I, seed=3)["init"], smps[0]["H"], smps[0]["W"],
+                             return_all=True, trace_cap=64)
+    print("traced", int((tr["trace"][..., 15] > 0).sum()))
     x = np.zeros((S, 6)); x[:, 0] = 0.1; x[:, 3] = 1.0
     prep = frustum.prepare_batch(xyz_in, pred_in, n, I, seed=3, sort=False)
     c, g, A = frustum.evaluate_batch(prep["xyz"], prep["label"], prep["n_pts"], smps[0]["K"], x, smps[0]["H"], smps[0]["W"], True)

@@ -271,6 +271,7 @@ def main():
     hybrid_jobs += in_gate[:: max(1, len(in_gate) // max(1, args.hybrid_in_gate))][:args.hybrid_in_gate]
     from deepi2p_b200 import _native
     slice_after = _native.load().frustum_solve_slice_after(S, I, 1 if is_2d else 0, 0)
+    slice_rounds = _native.load().frustum_solve_slice_rounds(S, I, 1 if is_2d else 0, 0)
     hyb = {"slice_after_of_the_traced_solve": slice_after, "solves": 0, "bit_identical_final_params": 0, "within_gate": 0, "identical_trace_points": 0, "rows": []}
     for k in hybrid_jobs:
         s, i = jobs[k]
@@ -280,7 +281,7 @@ def main():
         calls = [0]
 
         def ext(x6, xs=xs, ls_=ls_, ns_=ns_, calls=calls):
-            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d, sliced=calls[0] >= slice_after)
+            c, gr, A = frustum.evaluate_batch(xs, ls_, ns_, K, x6[None], H, W, is_2d, slice_rounds=(slice_rounds if calls[0] >= slice_after else 0))
             calls[0] += 1                 # the oracle evaluates in the same order as the kernel counts its passes
             return float(c[0]), gr[0].cpu().numpy(), A[0].cpu().numpy()
 
