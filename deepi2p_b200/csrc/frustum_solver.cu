@@ -1577,6 +1577,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         if (rc == LM_INTERP) {                      // warp-collective: interpolated line-search step size
           const LMState<P>& st = me.lm;
           const double step = interp_min_step_warp(st.lower, st.prev, st.cur, 1e-3 * st.cur.x, 0.6 * st.cur.x, lane);
+          __syncwarp();                             // every lane is done reading the samples before lane 0 rewrites them
           if (lane == 0) rc = lm_consume_step<P>(me.lm, step, false);
         }
         if (lane == 0) {

@@ -374,6 +374,33 @@ def test_one_call_path_and_traces(cuda):
     assert total >= S * I - 2 and agree >= total - 1
 
 
+def test_helped_passes_are_reproducible(cuda):
+    """Six full-size problems on six CTAs: every pass is cut into 10 slices and the 19 idle warps of each CTA race for
+    them.  Which warp computes which slice changes from run to run; the results must not (a slice's sum depends only
+    on the cloud, the pose and the slice, and the slice sums are added in slice order)."""
+    S, I = 2, 3
+    smps = [syn.make_sample(820 + s) for s in range(S)]
+    xyz_in, pred_in, _ = frustum.pack_clouds(np.stack([s["points"] for s in smps]), np.stack([s["pred"] for s in smps]))
+    K, H, W = smps[0]["K"], smps[0]["H"], smps[0]["W"]
+    ref = frustum.register_batch(xyz_in, pred_in, 20480, K, H, W, n_inits=I, seed=5, return_all=True)
+    ref = {k: v.clone() for k, v in ref.items()}
+    for _ in range(12):
+        out = frustum.register_batch(xyz_in, pred_in, 20480, K, H, W, n_inits=I, seed=5, return_all=True)
+        for key in ("P", "cost", "params", "costs", "stats"):
+            assert torch.equal(out[key], ref[key]), key
+    # and the sums of such a helped pass are the ones frustum_evaluate forms with the same slicing
+    from deepi2p_b200 import _native
+    lib = _native.load()
+    assert lib.frustum_solve_slice_after(S, I, 1, 0) == 0
+    rounds = lib.frustum_solve_slice_rounds(S, I, 1, 0)
+    prep = frustum.prepare_batch(xyz_in, pred_in, 20480, I, seed=5)
+    x = ref["params"][:, int(ref["best"][0])].contiguous()
+    c, _, _ = frustum.evaluate_batch(prep["xyz"], prep["label"], prep["n_pts"], K, x, H, W, True, slice_rounds=rounds)
+    for s in range(S):
+        if int(ref["best"][s]) == int(ref["best"][0]):
+            assert c[s].item() == ref["costs"][s, int(ref["best"][0])].item()      # bit for bit
+
+
 def test_full_size_properties(cuda):
     """BASELINE-size cloud (20480 points): size-independent properties instead of the oracle --
     the returned cost equals a fresh evaluation at the returned pose, the cost never exceeds the

@@ -220,3 +220,28 @@ def test_oracle_reproduces_committed_golden_vectors():
     np.testing.assert_array_equal(ca["count"], g["ca_count"])
     np.testing.assert_array_equal(ca["cluster_mean"], g["ca_mean"])
     np.testing.assert_array_equal(ca["pc_decentered"], g["ca_decentered"])
+
+
+def test_oracle_parity_tooling_options():
+    """The oracle's parity-tooling switches (off by default): the Cholesky linear solver lands on the QR solution of a
+    well-conditioned solve, the external-evaluation hook fed with the oracle's own sums reproduces the Cholesky run bit
+    for bit, and the trace holds one record per evaluation with the decisions the statistics report."""
+    smp = syn.make_sample(4300, n_points=1500)
+    iy, pf, lf, _ = oracle.initial_guess(smp["points"], smp["pred"])
+    ry, t = syn.make_inits(4300, iy, 2)
+    args = (pf, lf, smp["K"], ry[0], t[0], smp["H"], smp["W"], syn.T_LB, syn.T_UB, 500, True)
+    qr = oracle.solve(*args, want_residuals=False, trace_cap=400)
+    ch = oracle.solve(*args, want_residuals=False, linear_solver=1, trace_cap=400)
+    assert qr[3]["termination"] in (0, 1, 2) and len(qr[5]) == qr[3]["unique_evals"]
+    assert qr[5][0, 10] == 0 and qr[5][-1, 12] == qr[3]["termination"]
+    assert np.all(qr[5][:-1, 12] == -1)                       # only the last evaluation ends the solve
+    assert int(qr[5][:, 11].sum()) == qr[3]["successful_steps"] + 1   # accepted evaluations = successful steps + the start
+    np.testing.assert_allclose(ch[4], qr[4], rtol=0, atol=1e-6)
+
+    def ext(x6):
+        return oracle.evaluate(pf, lf, smp["K"], x6[:4], smp["H"], smp["W"], True)
+
+    hy = oracle.solve(*args, linear_solver=1, ext_eval=ext, trace_cap=400)
+    assert np.array_equal(hy[4], ch[4]) and hy[3] == ch[3] and np.array_equal(hy[5][:, :13], ch[5][:, :13])
+    with pytest.raises(ValueError):
+        oracle.solve(*args, ext_eval=ext)                     # the hook has no Jacobian rows: it needs linear_solver=1
