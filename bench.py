@@ -70,7 +70,7 @@ def load_measured_peaks():
 def load_traffic(S_local, n_inits, is_2d):
     """DRAM bytes (read + write) of ONE launch of the dominant kernel, from the committed ncu --set full capture
     (profiles/r01_traffic.json, written by scripts/ncu_traffic.py) -- only if it was taken on this workload."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
@@ -82,15 +82,22 @@ def load_traffic(S_local, n_inits, is_2d):
 
 
 def load_ncu_fractions(S_local, n_inits, is_2d):
-    """FP64-pipe and issue-slot utilisation of the dominant kernel from the same committed ncu capture (SURVEY 8d asks
-    for the FP64-ALU fraction next to the bandwidth fraction); None when the capture is of another workload."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    """What the committed ncu --set full capture of the dominant kernel says about its limiter (SURVEY 8d asks for the
+    FP64-ALU fraction next to the bandwidth fraction; VERDICT r1 for l2 / issue / dram as well); None when the capture
+    is of another workload."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     try:
         with open(p) as f:
             t = json.load(f)
         if t["samples_per_gpu"] == S_local and t["inits"] == n_inits and bool(t["is_2d"]) == bool(is_2d):
-            return {"fp64_pipe_active_pct": t.get("fp64_pipe_active_pct"), "issue_active_pct": t.get("issue_active_pct"),
-                    "source": "profiles/r01_traffic.json (%s)" % t.get("source")}
+            secs = t["gpu_time_ns"] * 1e-9
+            l2_bytes = t.get("lts_t_bytes") or ((t.get("l2_read_sectors_from_l1") or 0) * 32.0)
+            return {"issue_frac": (t.get("issue_active_pct") or 0) / 100.0, "fp64_frac": (t.get("fp64_pipe_active_pct") or 0) / 100.0,
+                    "dram_frac": (t.get("dram_throughput_pct") or 0) / 100.0,
+                    "l2_to_l1_GBps": l2_bytes / secs / 1e9 if secs > 0 else None,
+                    "warps_active_frac": (t.get("warps_active_pct") or 0) / 100.0,
+                    "lts_t_bytes": t.get("lts_t_bytes"), "dram_bytes": t["dram_bytes_read"] + t["dram_bytes_write"],
+                    "source": "profiles/r02_traffic.json (%s)" % t.get("source")}
     except Exception:  # noqa: BLE001
         pass
     return None

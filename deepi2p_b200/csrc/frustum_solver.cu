@@ -416,39 +416,37 @@ struct ClassConst {
   int enabled;
 };
 
-__device__ __noinline__ void make_class(const PoseConst& pc, const Cam& cam, ClassConst* cc) {
+// Warp-collective (all 32 lanes call): lane l < 20 computes coefficient l of the five forms (form l >> 2, column
+// l & 3, column 3 = the constant term); the error-margin scales are shuffle reductions (max is exact in any order).
+__device__ __forceinline__ void make_class(const PoseConst& pc, const Cam& cam, ClassConst* cc, int lane) {
   const double gamma = 8.0 / 16777216.0;    // 8 * 2^-24
   // the five forms kx X + ky Y + kz Z:  Z;  fx X + cx Z;  fx X + (cx - W1) Z;  fy Y + cy Z;  fy Y + (cy - H1) Z
-  const double kx[5] = {0.0, cam.fx, cam.fx, 0.0, 0.0};
-  const double ky[5] = {0.0, 0.0, 0.0, cam.fy, cam.fy};
-  const double kz[5] = {1.0, cam.cx, cam.cx - cam.W1, cam.cy, cam.cy - cam.H1};
-  double R[9], t[3];
-#pragma unroll
-  for (int j = 0; j < 9; ++j) R[j] = pc.R[j];
-#pragma unroll
-  for (int j = 0; j < 3; ++j) t[j] = pc.t[j];
-  float* out = cc->zc;                       // zc, al, ah, bl, bh are contiguous float[4]
-  double amax = 0.0, cmax = 0.0;
-  float fsum = 0.0f;                         // stays finite iff every coefficient is
-#pragma unroll
-  for (int f = 0; f < 5; ++f) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      const double c = fma(kx[f], R[j], fma(ky[f], R[3 + j], kz[f] * R[6 + j]));
-      amax = fmax(amax, fabs(c));
-      const float cf = (float)c;
-      fsum += fabsf(cf);
-      out[4 * f + j] = cf;
-    }
-    const double c3 = fma(kx[f], t[0], fma(ky[f], t[1], kz[f] * t[2]));
-    cmax = fmax(cmax, fabs(c3));
-    const float c3f = (float)c3;
-    fsum += fabsf(c3f);
-    out[4 * f + 3] = c3f;
+  const int f = lane >> 2, j = lane & 3;
+  double c = 0.0;
+  if (lane < 20) {
+    const double kx = (f == 1 || f == 2) ? cam.fx : 0.0;
+    const double ky = (f >= 3) ? cam.fy : 0.0;
+    const double kz = (f == 0) ? 1.0 : (f == 1) ? cam.cx : (f == 2) ? cam.cx - cam.W1 : (f == 3) ? cam.cy : cam.cy - cam.H1;
+    const double a0 = (j < 3) ? pc.R[j] : pc.t[0];
+    const double a1 = (j < 3) ? pc.R[3 + j] : pc.t[1];
+    const double a2 = (j < 3) ? pc.R[6 + j] : pc.t[2];
+    c = fma(kx, a0, fma(ky, a1, kz * a2));
   }
-  cc->G = (float)(gamma * amax * 1.0000002);
-  cc->G0 = (float)(gamma * cmax * 1.0000002) + 1e-30f;
-  cc->enabled = (isfinite(fsum) && isfinite(cc->G) && isfinite(cc->G0)) ? 1 : 0;
+  const float cf = (float)c;
+  if (lane < 20) cc->zc[lane] = cf;           // zc, al, ah, bl, bh are contiguous float[4]
+  double amax = (lane < 20 && j < 3) ? fabs(c) : 0.0;      // largest coefficient of (x, y, z)
+  double cmax = (lane < 20 && j == 3) ? fabs(c) : 0.0;     // largest constant term
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    cmax = fmax(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+  }
+  const bool finite = __all_sync(0xffffffffu, isfinite(cf));
+  if (lane == 0) {
+    cc->G = (float)(gamma * amax * 1.0000002);
+    cc->G0 = (float)(gamma * cmax * 1.0000002) + 1e-30f;
+    cc->enabled = (finite && isfinite(cc->G) && isfinite(cc->G0)) ? 1 : 0;
+  }
 }
 
 template <int P>
@@ -499,9 +497,6 @@ constexpr int kBoxRoundFloats = kBoxFields * kRoundGroups;
 #endif
 #ifndef DIB_GPS
 #define DIB_GPS 2                             // undecided groups fetched + classified per step
-#endif
-#ifndef DIB_GROUP_PIPE
-#define DIB_GROUP_PIPE 0                      // 1: the loads of the next step's groups are issued before this step's are used
 #endif
 #ifndef DIB_SLICE_ROUNDS
 #define DIB_SLICE_ROUNDS 4                    // rounds (of 1024 points) per slice: 20480 points = 20 rounds = 5 slices
@@ -734,7 +729,6 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
     // Undecided groups are taken DIB_GPS at a time.  Their loads are issued first, then the pending
     // exact-path batches are drained WHILE THE LOADS ARE IN FLIGHT, then the groups are classified
     // (independent instruction streams) and appended.  Ring bound: < kBatch carried + 32 x DIB_GPS new.
-#pragma unroll 1
     // take the next DIB_GPS groups (surely-active ones first: a step made only of them skips the classification,
     // then the undecided ones) and issue their loads
     auto take_groups = [&](CT* lx, CT* ly, CT* lz, int* ll, bool& sure_only) -> bool {
@@ -756,26 +750,15 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
       }
       return any;
     };
-#if DIB_GROUP_PIPE
-    // register software pipeline: the loads of the NEXT step are in flight while this step is drained / classified
-    CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
-    int glab[DIB_GPS];
-    bool all_sure = true;
-    bool have = take_groups(gx, gy, gz, glab, all_sure);
-#endif
 #pragma unroll 1
     do {
-#if DIB_GROUP_PIPE
-      CT nx[DIB_GPS], ny[DIB_GPS], nz[DIB_GPS];
-      int nlab[DIB_GPS];
-      bool nsure = true;
-      const bool nhave = take_groups(nx, ny, nz, nlab, nsure);
-#else
+      // (issuing the NEXT step's loads before this step is classified -- a register software pipeline -- measured
+      // 12 % slower on B200, 87.1 vs 77.6 ms per 512 x 60 problems: the registers it needs cost more than the latency
+      // it hides; profiles/r02_sweep_schedule.jsonl)
       CT gx[DIB_GPS], gy[DIB_GPS], gz[DIB_GPS];
       int glab[DIB_GPS];
       bool all_sure = true;
       const bool have = take_groups(gx, gy, gz, glab, all_sure);
-#endif
 #pragma unroll 1
       while (pend0 >= threshold) {
         __syncwarp();
@@ -828,17 +811,7 @@ __device__ __forceinline__ void eval_slice(WarpScratch<CT, P>& ws, const ProbCtx
           pend1 += __popc(m1);
         }
       }
-#if DIB_GROUP_PIPE
-      have = nhave;
-      all_sure = nsure;
-      if (nhave) {
-#pragma unroll
-        for (int u = 0; u < DIB_GPS; ++u) { gx[u] = nx[u]; gy[u] = ny[u]; gz[u] = nz[u]; glab[u] = nlab[u]; }
-      }
-    } while (have);
-#else
     } while (mask | mask_sure);
-#endif
   }
   acc[0] = 0.5 * (log(prod) + (double)expo * 0.6931471805599453094);
 
@@ -1440,11 +1413,18 @@ __device__ __forceinline__ void st_volatile(int* p, int v) { *reinterpret_cast<v
 template <typename CT, int P>
 __device__ __forceinline__ void open_pass(Smem<CT, P>& sm, ProbCtx<CT, P>& me, int warp, int slice_after) {
   const bool sliced = me.lm.evals >= slice_after;
+  // Close the counter before the slice layout changes: after a pass next_slice equals the OLD slice count, which is
+  // below the new one when a problem goes from one-piece to sliced passes -- a helper polling in that window would
+  // claim a slice of a pass that is not open yet (and be counted twice).
+  st_volatile(&me.next_slice, 0x3fffffff);
+  __threadfence_block();
   me.nslices = sliced ? me.nslices_full : 1;
   me.slice_rounds = sliced ? me.len_full : (me.rounds > 0 ? me.rounds : 1);
   st_volatile(&me.done, 0);
-  __threadfence_block();                       // pose, cls, done before the pass becomes claimable
-  atomicOr(&sm.open_mask, 1u << warp);         // bit first: whoever claims the last slice clears it again
+  __threadfence_block();                       // pose, cls, layout, done before the pass becomes claimable
+  // only a pass with more than one slice is advertised: a one-piece pass is its owner's alone (a "helper" would just
+  // take the whole pass away while the owner waits)
+  if (me.nslices > 1) atomicOr(&sm.open_mask, 1u << warp);   // bit first: whoever claims the last slice clears it again
   st_volatile(&me.next_slice, 0);
 }
 
@@ -1482,7 +1462,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ProbCtx<CT, P>& me = sm.ctx[warp];
   WarpScratch<CT, P>& ws = sm.scratch[warp];
-  if (lane == 0) { me.next_slice = 0; me.nslices = 0; me.done = 0; me.prob = -1; }
+  if (lane == 0) { me.next_slice = 0x3fffffff; me.nslices = 0; me.done = 0; me.prob = -1; }
   if (threadIdx.x == 0) { sm.open_mask = 0u; sm.n_active = kW; }
   // Launch timeline for the benchmark (three 64-bit words after the queue counter, zeroed / primed by the host):
   // kernel start, the moment the queue ran dry, the last CTA's exit -- all in globaltimer nanoseconds.
@@ -1530,19 +1510,57 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         make_cam(a.K9 + (size_t)s * 9, a.H, a.W, &me.cam);
         rc = lm_begin<P>(me.lm, a.init + (size_t)prob * 4, a.lb, a.ub, a.max_iter);
         n_rec = 0;
-        if (rc == LM_EVAL) { make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls); open_pass<CT, P>(sm, me, warp, a.slice_after); }
+        if (rc == LM_EVAL) make_pose<P>(me.lm.xt, &me.pose);
       }
       __syncwarp();                                     // lane 0's problem set-up is visible to the whole warp
       rc = __shfl_sync(0xffffffffu, rc, 0);
+      if (rc == LM_EVAL) {
+        make_class(me.pose, me.cam, &me.cls, lane);
+        __syncwarp();
+        if (lane == 0) open_pass<CT, P>(sm, me, warp, a.slice_after);
+        __syncwarp();
+      }
       state = (rc == LM_EVAL) ? ST_RUN : ST_FETCH;        // lm_begin always asks for an evaluation today
       continue;
     }
 
-    // ---- pick a slice: one of mine first, else one of a CTA-mate's open pass ----
+    // ---- pick a slice: my own finished pass first, then a slice of mine, else any open pass of a CTA-mate ----
+    // (taking the open slices of OLD problems before a warp's own work -- "oldest first" -- measured no gain, 79.1 vs
+    // 78.5 ms: the end-of-kernel tail is in-flight work draining at falling occupancy, not old problems running slowly)
     int owner = -1, k = 0, r_begin = 0, r_end = 0;
+    // lane 0 tries to claim a slice of the lowest-numbered warp in `m`; returns the warp (or -1) and the slice in kk
+    auto try_claim = [&](unsigned m, int& kk) -> int {
+      int o = -1;
+      if (lane == 0 && m) {
+        const int cand = __ffs(m) - 1;
+        ProbCtx<CT, P>& oc = sm.ctx[cand];
+        if (ld_volatile(&oc.next_slice) < ld_volatile(&oc.nslices)) {
+          const int got = atomicAdd(&oc.next_slice, 1);
+          __threadfence_block();
+          const int ns = ld_volatile(&oc.nslices);        // re-read after the claim: the pass cannot change under a valid claim
+          if (got < ns) {
+            o = cand; kk = got;
+            if (got == ns - 1) atomicAnd(&sm.open_mask, ~(1u << cand));
+          }
+        }
+      }
+      __syncwarp();
+      o = __shfl_sync(0xffffffffu, o, 0);
+      kk = __shfl_sync(0xffffffffu, kk, 0);
+      return o;
+    };
+    // my own finished pass comes first: only I can take its control step, and it is the serial part of my problem
+    int complete = 0;
     if (state == ST_RUN) {
-      int mine = -1, complete = 0;
       if (lane == 0) {
+        const int ns = me.nslices;
+        complete = (ld_volatile(&me.next_slice) >= ns && ld_volatile(&me.done) == ns) ? 1 : 0;
+      }
+      complete = __shfl_sync(0xffffffffu, complete, 0);
+    }
+    if (owner < 0 && state == ST_RUN) {
+      int mine = -1;
+      if (lane == 0 && !complete) {
         const int ns = me.nslices;
         if (ld_volatile(&me.next_slice) < ns) {
           const int kk = atomicAdd(&me.next_slice, 1);
@@ -1551,10 +1569,8 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
             if (kk == ns - 1) atomicAnd(&sm.open_mask, ~(1u << warp));
           }
         }
-        if (mine < 0 && ld_volatile(&me.done) == ns) complete = 1;
       }
       mine = __shfl_sync(0xffffffffu, mine, 0);
-      complete = __shfl_sync(0xffffffffu, complete, 0);
       if (mine >= 0) {
         owner = warp; k = mine;
       } else if (complete) {
@@ -1584,8 +1600,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
           trace_record<CT, P>(a, me, n_rec, true);
           ++n_rec;
           if (rc == LM_EVAL) {
-            make_pose<P>(me.lm.xt, &me.pose); make_class(me.pose, me.cam, &me.cls);
-            open_pass<CT, P>(sm, me, warp, a.slice_after);
+            make_pose<P>(me.lm.xt, &me.pose);
           } else {
             const LMState<P>& st = me.lm;
             double* po = a.params_all + (size_t)me.prob * 6;
@@ -1597,32 +1612,22 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         }
         __syncwarp();
         rc = __shfl_sync(0xffffffffu, rc, 0);
-        if (rc != LM_EVAL) state = ST_FETCH;
+        if (rc == LM_EVAL) {
+          make_class(me.pose, me.cam, &me.cls, lane);
+          __syncwarp();
+          if (lane == 0) open_pass<CT, P>(sm, me, warp, a.slice_after);
+        } else {
+          state = ST_FETCH;
+        }
         continue;
       }
     }
     if (owner < 0) {
       // nothing of mine to do right now (idle, or waiting for helpers to finish my pass): help a CTA-mate
-      int o = -1, kk = 0;
-      if (lane == 0) {
-        const unsigned m = ld_volatile(&sm.open_mask) & ~(1u << warp);
-        if (m) {
-          const int cand = __ffs(m) - 1;
-          ProbCtx<CT, P>& oc = sm.ctx[cand];
-          if (ld_volatile(&oc.next_slice) < ld_volatile(&oc.nslices)) {
-            const int got = atomicAdd(&oc.next_slice, 1);
-            __threadfence_block();
-            const int ns = ld_volatile(&oc.nslices);      // re-read after the claim: the pass cannot change under a valid claim
-            if (got < ns) {
-              o = cand; kk = got;
-              if (got == ns - 1) atomicAnd(&sm.open_mask, ~(1u << cand));
-            }
-          }
-        }
-      }
-      __syncwarp();
-      o = __shfl_sync(0xffffffffu, o, 0);
-      kk = __shfl_sync(0xffffffffu, kk, 0);
+      unsigned m = 0;
+      if (lane == 0) m = ld_volatile(&sm.open_mask) & ~(1u << warp);
+      m = __shfl_sync(0xffffffffu, m, 0);
+      const int o = try_claim(m, k);
       if (o < 0) {
         if (state == ST_IDLE) {
           int na = 0;
@@ -1640,7 +1645,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         __nanosleep(state == ST_IDLE ? 400 : 100);
         continue;
       }
-      owner = o; k = kk;
+      owner = o;
     }
     ProbCtx<CT, P>& oc = sm.ctx[owner];
     {
@@ -1741,8 +1746,9 @@ __global__ void __launch_bounds__(kEvalWarps * 32) frustum_evaluate_kernel(const
     pb.nslices = rounds > 0 ? (rounds + len - 1) / len : 1;
     make_cam(K9 + (size_t)s * 9, H, W, &pb.cam);
     make_pose<P>(x + (size_t)s * 6, &pb.pose);
-    make_class(pb.pose, pb.cam, &pb.cls);
   }
+  __syncthreads();
+  if (warp == 0) make_class(pb.pose, pb.cam, &pb.cls, lane);
   __syncthreads();
   const int ns = pb.nslices, len = pb.slice_rounds, rounds = pb.rounds;
   for (int k = warp; k < ns; k += kEvalWarps) {
@@ -1805,6 +1811,7 @@ static size_t packed_bytes(int S, int n_stride) {
 #ifndef DIB_SLICE_AFTER
 #define DIB_SLICE_AFTER 48
 #endif
+
 static int default_slice_after() {
   static const int v = [] {
     const char* e = getenv("DIB_SLICE_AFTER");           // tuning knob; results depend on it at rounding level only
@@ -1903,6 +1910,7 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   long long grid = (long long)cfg.sms * cfg.per_sm;
   a.slice_after = slice_after_for(total, grid * kW);
   a.slice_rounds = slice_rounds_for(a.slice_after);
+
   if (grid > total) grid = total;
   // scheduling chunk: the queue walks chunks of samples rank-major (longest-predicted inits of every sample of the
   // chunk first).  Larger chunks start the long solves earlier (shorter tail); smaller chunks keep the packed clouds

@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 for item in "$@"; do
   flags="${item%%|*}"; envs="${item#*|}"
   DIB_NVCC_EXTRA="$flags" python -m deepi2p_b200.build --force > /dev/null 2>&1 || { echo "BUILD FAILED: $flags"; continue; }
-  env $envs python bench.py ${BENCH_ARGS:-} --steps 4 --warmup 2 --no-cpu-baseline --no-configs --samples-per-gpu ${SWEEP_SAMPLES:-512} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err || { echo "RUN FAILED: $item"; tail -3 gpurun_out/sweep_tmp.err; continue; }
+  env $envs timeout 150 python bench.py ${BENCH_ARGS:-} --steps 4 --warmup 2 --no-cpu-baseline --no-configs --samples-per-gpu ${SWEEP_SAMPLES:-512} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err || { echo "RUN FAILED: $item"; tail -3 gpurun_out/sweep_tmp.err; continue; }
   python - "$item" <<'PY'
 import json, sys
 d = json.load(open("gpurun_out/sweep_tmp.json")); r = d["roofline"]

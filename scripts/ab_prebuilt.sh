@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 for item in "$@"; do
   name="${item%%|*}"; envs=""; [ "$item" != "$name" ] && envs="${item#*|}"     # "variant|ENV=val ENV2=val"
   lib=""; [ "$name" != default ] && lib="deepi2p_b200/lib/variants/$name.so"
-  env DIB_LIB_OVERRIDE="$lib" $envs python bench.py ${BENCH_ARGS:-} --steps 4 --warmup 2 --no-cpu-baseline --no-configs --samples-per-gpu ${SWEEP_SAMPLES:-512} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err || { echo "RUN FAILED: $name"; tail -3 gpurun_out/sweep_tmp.err; continue; }
+  env DIB_LIB_OVERRIDE="$lib" $envs timeout 150 python bench.py ${BENCH_ARGS:-} --steps 4 --warmup 2 --no-cpu-baseline --no-configs --samples-per-gpu ${SWEEP_SAMPLES:-512} > gpurun_out/sweep_tmp.json 2> gpurun_out/sweep_tmp.err || { echo "RUN FAILED: $name"; tail -3 gpurun_out/sweep_tmp.err; continue; }
   python - "$item" <<'PY'
 import json, sys
 d = json.load(open("gpurun_out/sweep_tmp.json")); r = d["roofline"]

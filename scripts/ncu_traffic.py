@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Extract DRAM traffic of the solve kernel from an ncu report into profiles/r01_traffic.json.
-   python scripts/ncu_traffic.py gpurun_out/prof_X_solve.ncu-rep <samples_per_gpu> <inits> <is_2d 0|1>"""
+"""Extract DRAM / L2 traffic and pipe fractions of the solve kernel from an ncu report into profiles/r02_traffic.json.
+   python scripts/ncu_traffic.py gpurun_out/prof_X_solve.ncu-rep <samples_per_gpu> <inits> <is_2d 0|1> [out.json]"""
 import csv, io, json, os, subprocess, sys
 rep, S, I, is2d = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -22,8 +22,12 @@ def pct(name):
 # the FP64-ALU fraction is reported next to the bandwidth fraction
 out["fp64_pipe_active_pct"] = pct("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active")
 out["issue_active_pct"] = pct("smsp__issue_active.avg.pct_of_peak_sustained_active")
+out["warps_active_pct"] = pct("sm__warps_active.avg.pct_of_peak_sustained_active")
+out["l2_read_sectors_from_l1"] = pct("lts__t_sectors_srcunit_tex_op_read.sum")
+out["dram_throughput_pct"] = pct("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed")
 out["registers_per_thread"] = pct("launch__registers_per_thread")
 out["grid_size"] = pct("launch__grid_size")
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-json.dump(out, open(os.path.join(root, "profiles", "r01_traffic.json"), "w"), indent=1)
+dst = sys.argv[5] if len(sys.argv) > 5 else os.path.join(root, "profiles", "r02_traffic.json")
+json.dump(out, open(dst, "w"), indent=1)
 print(out)
