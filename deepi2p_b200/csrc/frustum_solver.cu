@@ -41,23 +41,27 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// Warps per CTA (= problems in flight per SM; one CTA per SM).  The register budget decides: 20 warps x 32
-// lanes x 96 registers for the 4-DoF solver, fewer for 6-DoF (128 registers) and for the f64 record (rings
-// twice as large); shared memory (rings + accumulators + per-problem state) is checked below.
+// Team shape: warps per CTA (= the help domain: warps that can take slices of each other's passes) x CTAs per SM
+// (= problems in flight per SM / warps per CTA).  The register budget decides the product: 20 warps x 32 lanes x 96
+// registers for the 4-DoF solver, 14 for 6-DoF (128 registers) and for the f64 record (rings twice as large); shared
+// memory (rings + accumulators + per-problem state, ~10.6 KB per 4-DoF warp) is checked below.  Measured on B200, 512 x
+// 60 problems (profiles/r02_sweep_schedule.jsonl): 20 x 1: 77.5 ms, 10 x 2: 76.8, 5 x 4: 76.5, 4 x 5: 76.7 -- smaller
+// CTAs leave the SM earlier at the end of a launch (the next launch's CTAs start there); 10 x 2 keeps a help domain of
+// 10 warps, which is what a small batch's 10 slices per pass can use.
 #ifndef DIB_WARPS_F4
-#define DIB_WARPS_F4 20
+#define DIB_WARPS_F4 10
 #endif
 #ifndef DIB_WARPS_F6
-#define DIB_WARPS_F6 14
+#define DIB_WARPS_F6 7
 #endif
 #ifndef DIB_WARPS_D4
-#define DIB_WARPS_D4 14
+#define DIB_WARPS_D4 7
 #endif
 #ifndef DIB_WARPS_D6
-#define DIB_WARPS_D6 10
+#define DIB_WARPS_D6 5
 #endif
 #ifndef DIB_CTAS_PER_SM
-#define DIB_CTAS_PER_SM 1                     // tuning: e.g. 10 warps x 2 CTAs (smaller help domain, same warps per SM)
+#define DIB_CTAS_PER_SM 2
 #endif
 template <typename CT, int P> struct Cfg;
 template <> struct Cfg<float, 4> { static constexpr int kWarps = DIB_WARPS_F4; };
