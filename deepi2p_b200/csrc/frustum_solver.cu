@@ -631,6 +631,7 @@ struct ProbCtx {
   const float* box;                       // its box table
   int rounds, slice_rounds, nslices;      // of the OPEN pass (a young problem's pass is one slice, see open_pass)
   int len_full, nslices_full;             // the cloud's fixed slicing, used from pass number slice_after on
+  int slice_after;                        // this problem's first sliced pass (0 for the late problems of a batch)
   int prob;
   int next_slice;                         // claim counter of the open pass (>= nslices: nothing left to claim)
   int done;                               // slices of the open pass that are finished
@@ -1366,6 +1367,8 @@ struct SolveArgs {
   int chunk;            // samples per scheduling chunk
   int slice_rounds;     // rounds per slice (before the kMaxSlices stretch)
   int slice_after;      // passes of a problem that run as ONE slice before the fixed slicing starts
+  int late_from;        // queue positions >= late_from are LATE problems: sliced from their first pass, in
+  int late_slice_rounds; // slices of late_slice_rounds rounds (they run while the batch drains: help is there from the start)
   double* trace;        // optional [S*I][trace_cap][kTraceRec] per-evaluation records, or NULL
   int trace_cap;
 };
@@ -1415,8 +1418,8 @@ __device__ __forceinline__ void st_volatile(int* p, int v) { *reinterpret_cast<v
 // the end-of-kernel tail can be helped.  The switch depends on the problem's own pass count only, so results stay
 // independent of the batch, of the schedule and of who helps.
 template <typename CT, int P>
-__device__ __forceinline__ void open_pass(Smem<CT, P>& sm, ProbCtx<CT, P>& me, int warp, int slice_after) {
-  const bool sliced = me.lm.evals >= slice_after;
+__device__ __forceinline__ void open_pass(Smem<CT, P>& sm, ProbCtx<CT, P>& me, int warp) {
+  const bool sliced = me.lm.evals >= me.slice_after;
   // Close the counter before the slice layout changes: after a pass next_slice equals the OLD slice count, which is
   // below the new one when a problem goes from one-piece to sliced passes -- a helper polling in that window would
   // claim a slice of a pass that is not open yet (and be counted twice).
@@ -1504,7 +1507,9 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
       if (lane == 0) {
         const int n = a.n_pts ? a.n_pts[s] : a.n_stride;
         const int rounds = box_rounds(n);
-        const int len = slice_len(rounds, a.slice_rounds);
+        const bool late = q >= a.late_from;
+        const int len = slice_len(rounds, late ? a.late_slice_rounds : a.slice_rounds);
+        me.slice_after = late ? 0 : a.slice_after;
         me.prob = prob;
         me.pk = reinterpret_cast<const Entry<CT>*>(a.packed) + (size_t)s * a.rounds_max * kRoundPoints;
         me.box = a.boxes + (size_t)s * a.rounds_max * kBoxRoundFloats;
@@ -1521,7 +1526,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
       if (rc == LM_EVAL) {
         make_class(me.pose, me.cam, &me.cls, lane);
         __syncwarp();
-        if (lane == 0) open_pass<CT, P>(sm, me, warp, a.slice_after);
+        if (lane == 0) open_pass<CT, P>(sm, me, warp);
         __syncwarp();
       }
       state = (rc == LM_EVAL) ? ST_RUN : ST_FETCH;        // lm_begin always asks for an evaluation today
@@ -1619,7 +1624,7 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         if (rc == LM_EVAL) {
           make_class(me.pose, me.cam, &me.cls, lane);
           __syncwarp();
-          if (lane == 0) open_pass<CT, P>(sm, me, warp, a.slice_after);
+          if (lane == 0) open_pass<CT, P>(sm, me, warp);
         } else {
           state = ST_FETCH;
         }
@@ -1914,6 +1919,18 @@ static int launch_solve(const SolveArgs& a_in, cudaStream_t st) {
   long long grid = (long long)cfg.sms * cfg.per_sm;
   a.slice_after = slice_after_for(total, grid * kW);
   a.slice_rounds = slice_rounds_for(a.slice_after);
+  // The last problems of a large batch start while the batch drains: CTA-mates go idle within their first passes, so
+  // they are sliced from their first pass on (in the short slices of a small batch) instead of from pass slice_after.
+  // "Last" is a queue position, and the queue order is a function of the batch alone: results stay reproducible.
+  {
+    long long late = a.slice_after > 0 ? grid * kW : 0;
+    if (const char* e = getenv("DIB_LATE_PROBLEMS")) late = atoll(e);   // tuning knob
+    if (late < 0) late = 0;
+    if (late > total) late = total;
+    a.late_from = (int)(total - late);
+    a.late_slice_rounds = slice_rounds_for(0);
+    if (const char* e = getenv("DIB_LATE_SLICE_ROUNDS")) a.late_slice_rounds = atoi(e) > 0 ? atoi(e) : a.late_slice_rounds;
+  }
 
   if (grid > total) grid = total;
   // scheduling chunk: the queue walks chunks of samples rank-major (longest-predicted inits of every sample of the
@@ -1992,6 +2009,7 @@ static int solve_batch(const CT* xyz, const int8_t* label, const int32_t* n_pts,
   a.chunk = 1;
   a.slice_rounds = default_slice_rounds();
   a.slice_after = 0;                                   // decided in launch_solve (needs the grid)
+  a.late_from = 0x7fffffff; a.late_slice_rounds = a.slice_rounds;
   a.trace = trace; a.trace_cap = trace_cap;
   DIB_CHECK_CUDA(cudaMemsetAsync(a.queue, 0, kHeaderBytes, st));
   DIB_CHECK_CUDA(cudaMemsetAsync((unsigned char*)a.queue + 8, 0xff, 16, st));   // timeline minima start at ~0ull

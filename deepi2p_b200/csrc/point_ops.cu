@@ -16,6 +16,12 @@
 
 namespace dib {
 
+#ifndef DIB_IM_GLOBAL_KEYS
+#define DIB_IM_GLOBAL_KEYS 0
+#endif
+#ifndef DIB_IM_PRE_SHIFT
+#define DIB_IM_PRE_SHIFT 4      // the pre-pass seeds the thresholds from the first 2^-DIB_IM_PRE_SHIFT of the row
+#endif
 constexpr int kImThreads = 128;     // 4096 (b, channel-group) CTAs' worth of work stays co-resident: no wave tail
 
 __device__ __forceinline__ uint32_t ordered_bits(float v) {
@@ -43,15 +49,26 @@ __device__ __forceinline__ void im_consider(float* bestf, unsigned long long* be
 template <int CPB, bool VEC>
 __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __restrict__ data,
                                                                const int32_t* __restrict__ index,
-                                                               int32_t* __restrict__ out, int B, int C, int N, int K) {
+                                                               int32_t* __restrict__ out, int B, int C, int N, int K,
+                                                               unsigned long long* __restrict__ gkeys) {
   extern __shared__ __align__(16) unsigned char im_smem[];
-  unsigned long long* bestk = reinterpret_cast<unsigned long long*>(im_smem);
-  float* bestv = reinterpret_cast<float*>(bestk + (size_t)CPB * K);
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CPB;
   const int nc = min(CPB, C - c0);
+#if DIB_IM_GLOBAL_KEYS
+  // The winner keys of this CTA's (b, c0..c0+CPB) segments live in global memory (L2): the exact update is a native
+  // 64-bit RED.MAX there, where shared memory would need a compare-and-swap loop.  Only this CTA touches them.
+  unsigned long long* bestk = gkeys + ((size_t)b * C + c0) * K;
+  float* bestv = reinterpret_cast<float*>(im_smem);
+  for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = -1000.0f; }
+  __threadfence();
+  __syncthreads();
+#else
+  unsigned long long* bestk = reinterpret_cast<unsigned long long*>(im_smem);
+  float* bestv = reinterpret_cast<float*>(bestk + (size_t)CPB * K);
   for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = -1000.0f; }
   __syncthreads();
+#endif
   const int32_t* idx = index + (size_t)b * N;
   const float* rows = data + ((size_t)b * C + c0) * N;
 
@@ -63,7 +80,7 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
     // Every threshold is the value of a real element of its segment, so it can never exceed the
     // segment maximum, and the main pass below re-scans these elements with the full logic.
     {
-      const int npre = n4 >> 4;
+      const int npre = n4 >> DIB_IM_PRE_SHIFT;
       for (int i = threadIdx.x; i < npre; i += kImThreads) {
         const int4 kk = __ldg(reinterpret_cast<const int4*>(idx) + i);
         const int k4[4] = {kk.x, kk.y, kk.z, kk.w};
@@ -128,9 +145,16 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
         if (c < nc) im_consider<CPB>(bestv, bestk, K, c, k, __ldcs(rows + (size_t)c * N + i), (uint32_t)i);
     }
   }
+#if DIB_IM_GLOBAL_KEYS
+  __threadfence();                                 // this thread's REDs before the read-back below
+  __syncthreads();
+  for (int i = threadIdx.x; i < nc * K; i += kImThreads) {
+    const unsigned long long key = __ldcg(bestk + i);
+#else
   __syncthreads();
   for (int i = threadIdx.x; i < nc * K; i += kImThreads) {
     const unsigned long long key = bestk[i];
+#endif
     out[((size_t)b * C + c0) * K + i] = key ? (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)) : 0;
   }
 }
@@ -156,11 +180,13 @@ __device__ __forceinline__ void bq_scan(const float v[kBqHalf], float radius, in
   for (int j = 0; j < kBqHalf; ++j) {
     const bool hit = v[j] <= radius;
     const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      const int pos = cnt + __popc(m & ((1u << lane) - 1u));
-      if (pos < K) o[pos] = base + j * 32 + lane;
+    if (m) {                                       // warp-uniform; hits are rare
+      if (hit) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pos < K) o[pos] = base + j * 32 + lane;
+      }
+      cnt += __popc(m);
     }
-    cnt += __popc(m);
   }
 }
 
@@ -191,6 +217,37 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* 
   }
 }
 
+// 128-bit variant of bq_load / bq_scan for 16-byte aligned rows: kBqVec float4 per lane = 512 elements per warp and
+// half, lane l holding elements 4l .. 4l+3 of each 128-element block.  Hits are rare (K of N), so the common block
+// costs four compares, four ballots and one warp-uniform branch; only a block with a hit computes positions: the
+// hits of lower lanes (all four components) come first, then this lane's own lower components -- index order.
+constexpr int kBqVec = kBqHalf / 4;
+
+__device__ __forceinline__ void bq_load4(const float4* d4, int lane, float4 v[kBqVec]) {
+#pragma unroll
+  for (int j = 0; j < kBqVec; ++j) v[j] = __ldcs(d4 + j * 32 + lane);
+}
+
+__device__ __forceinline__ void bq_scan4(const float4 v[kBqVec], float radius, int base, int lane, int K, int32_t* o,
+                                         int& cnt) {
+#pragma unroll
+  for (int j = 0; j < kBqVec; ++j) {
+    const bool h0 = v[j].x <= radius, h1 = v[j].y <= radius, h2 = v[j].z <= radius, h3 = v[j].w <= radius;
+    const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+    const unsigned m2 = __ballot_sync(0xffffffffu, h2), m3 = __ballot_sync(0xffffffffu, h3);
+    if (m0 | m1 | m2 | m3) {                       // warp-uniform
+      const unsigned lt = (1u << lane) - 1u;
+      int pos = cnt + __popc(m0 & lt) + __popc(m1 & lt) + __popc(m2 & lt) + __popc(m3 & lt);
+      const int e = base + j * 128 + lane * 4;
+      if (h0) { if (pos < K) o[pos] = e; ++pos; }
+      if (h1) { if (pos < K) o[pos] = e + 1; ++pos; }
+      if (h2) { if (pos < K) o[pos] = e + 2; ++pos; }
+      if (h3) { if (pos < K) o[pos] = e + 3; }
+      cnt += __popc(m0) + __popc(m1) + __popc(m2) + __popc(m3);
+    }
+  }
+}
+
 // Row split over the 4 warps of a CTA (one CTA per row): each warp compacts its quarter of the row
 // into its own shared-memory list (at most K hits), then the lists are concatenated in order.  Four
 // times as many independent load streams as the warp-per-row kernel; used when 4 K ints fit in
@@ -198,6 +255,7 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* 
 // whose K-th hit comes early read more than they strictly need.
 constexpr int kBqSplit = 4;
 
+template <bool VEC>
 __global__ void __launch_bounds__(kBqSplit * 32) ball_query_split_kernel(const float* __restrict__ dist, float radius,
                                                                          int32_t* __restrict__ out, int N, int K) {
   extern __shared__ int32_t bq_hits[];          // [kBqSplit][K]
@@ -211,15 +269,31 @@ __global__ void __launch_bounds__(kBqSplit * 32) ball_query_split_kernel(const f
   int32_t* mine = bq_hits + w * K;
   constexpr int kStep = 32 * kBqHalf;
   int cnt = 0;
-  float va[kBqHalf], vb[kBqHalf];
-  if (lo < hi) {
-    bq_load(d, lo, hi, lane, va);
-    for (int base = lo; base < hi && cnt < K; base += 2 * kStep) {
-      if (base + kStep < hi) bq_load(d, base + kStep, hi, lane, vb);
-      bq_scan(va, radius, base, lane, K, mine, cnt);
-      if (cnt >= K || base + kStep >= hi) break;
-      if (base + 2 * kStep < hi) bq_load(d, base + 2 * kStep, hi, lane, va);
-      bq_scan(vb, radius, base + kStep, lane, K, mine, cnt);
+  if (VEC) {
+    // quarters are whole multiples of kStep elements and 16-byte aligned (checked by the host)
+    float4 va[kBqVec], vb[kBqVec];
+    if (lo < hi) {
+      const float4* d4 = reinterpret_cast<const float4*>(d);
+      bq_load4(d4 + (lo >> 2), lane, va);
+      for (int base = lo; base < hi && cnt < K; base += 2 * kStep) {
+        if (base + kStep < hi) bq_load4(d4 + ((base + kStep) >> 2), lane, vb);
+        bq_scan4(va, radius, base, lane, K, mine, cnt);
+        if (cnt >= K || base + kStep >= hi) break;
+        if (base + 2 * kStep < hi) bq_load4(d4 + ((base + 2 * kStep) >> 2), lane, va);
+        bq_scan4(vb, radius, base + kStep, lane, K, mine, cnt);
+      }
+    }
+  } else {
+    float va[kBqHalf], vb[kBqHalf];
+    if (lo < hi) {
+      bq_load(d, lo, hi, lane, va);
+      for (int base = lo; base < hi && cnt < K; base += 2 * kStep) {
+        if (base + kStep < hi) bq_load(d, base + kStep, hi, lane, vb);
+        bq_scan(va, radius, base, lane, K, mine, cnt);
+        if (cnt >= K || base + kStep >= hi) break;
+        if (base + 2 * kStep < hi) bq_load(d, base + 2 * kStep, hi, lane, va);
+        bq_scan(vb, radius, base + kStep, lane, K, mine, cnt);
+      }
     }
   }
   if (lane == 0) bq_cnt[w] = min(cnt, K);
@@ -251,24 +325,31 @@ int index_max_forward(const float* data, const int32_t* index, int32_t* out, int
   if (B == 0 || C == 0) return DIB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (N % 4 == 0) && ((uintptr_t)data % 16 == 0) && ((uintptr_t)index % 16 == 0);
-  const size_t per_c = (size_t)K * 12;
+  const size_t per_c = (size_t)K * (DIB_IM_GLOBAL_KEYS ? 4 : 12);
   const size_t limit = 227 * 1024;
   int cpb = 4;
   while (cpb > 1 && per_c * cpb > limit) cpb >>= 1;
   DIB_REQUIRE(per_c * cpb <= limit, "K=%d too large for the shared-memory segment table", K);
   const size_t smem = per_c * cpb;
   dim3 grid((C + cpb - 1) / cpb, B);
+  unsigned long long* gkeys = nullptr;
+#if DIB_IM_GLOBAL_KEYS
+  DIB_CHECK_CUDA(cudaMallocAsync((void**)&gkeys, (size_t)B * C * K * sizeof(unsigned long long), st));   // stream-ordered, pooled
+#endif
 #define DIB_IM_LAUNCH(CPB, VEC)                                                                              \
   do {                                                                                                       \
     auto kern = dib::index_max_kernel<CPB, VEC>;                                                             \
     DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kern<<<grid, dib::kImThreads, smem, st>>>(data, index, out, B, C, N, K);                                 \
+    kern<<<grid, dib::kImThreads, smem, st>>>(data, index, out, B, C, N, K, gkeys);                          \
   } while (0)
   if (cpb == 4) { if (vec) DIB_IM_LAUNCH(4, true); else DIB_IM_LAUNCH(4, false); }
   else if (cpb == 2) { if (vec) DIB_IM_LAUNCH(2, true); else DIB_IM_LAUNCH(2, false); }
   else { if (vec) DIB_IM_LAUNCH(1, true); else DIB_IM_LAUNCH(1, false); }
 #undef DIB_IM_LAUNCH
   DIB_CHECK_CUDA(cudaGetLastError());
+#if DIB_IM_GLOBAL_KEYS
+  DIB_CHECK_CUDA(cudaFreeAsync(gkeys, st));
+#endif
   return DIB_OK;
 }
 
@@ -282,7 +363,10 @@ int ball_query_forward(const float* dist, float radius, int32_t* out, int B, int
   cudaStream_t st = (cudaStream_t)stream;
   const size_t split_smem = (size_t)kBqSplit * K * sizeof(int32_t);
   if (split_smem <= 32 * 1024 && N >= 4096 && rows < (1ll << 31)) {
-    ball_query_split_kernel<<<(unsigned)rows, kBqSplit * 32, split_smem, st>>>(dist, radius, out, N, K);
+    // 128-bit loads when every quarter of every row is a 16-byte aligned whole number of 512-element steps
+    const bool vec = (N % (kBqSplit * 32 * kBqHalf) == 0) && ((uintptr_t)dist % 16 == 0);
+    if (vec) ball_query_split_kernel<true><<<(unsigned)rows, kBqSplit * 32, split_smem, st>>>(dist, radius, out, N, K);
+    else ball_query_split_kernel<false><<<(unsigned)rows, kBqSplit * 32, split_smem, st>>>(dist, radius, out, N, K);
   } else {
     const long long blocks = (rows + kBqWarps - 1) / kBqWarps;
     DIB_REQUIRE(blocks < (1ll << 31), "too many rows");

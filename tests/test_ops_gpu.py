@@ -150,6 +150,32 @@ def test_index_max_dropin_cpu_entry_points(cuda):
         im.forward_cpu(torch.zeros(1, 1, 4, device="cuda"), torch.zeros(1, 4, dtype=torch.int32, device="cuda"), 2)
 
 
+def test_ball_query_vector_path_adversarial(cuda):
+    """N a multiple of 2048 and an aligned matrix take the 128-bit path (lane l holds elements 4l..4l+3 of a
+    128-element block): hits in all four components of one lane, runs across lane / block / step / quarter
+    boundaries, every element a hit, K reached in mid-block, K - 1 hits, none, NaN."""
+    B, M, N, K = 1, 10, 8192, 24
+    dist = np.full((B, M, N), 7.0, dtype=np.float32)
+    dist[0, 0, 40:44] = 0.0                                        # the four components of lane 10
+    dist[0, 1, 126:131] = 1.0                                      # across a 128-element block boundary, inclusive <=
+    dist[0, 2, 509:515] = 0.0                                      # across a 512-element step boundary
+    dist[0, 3, 2046:2050] = 0.0                                    # across the first quarter boundary (2048)
+    dist[0, 4, :] = 0.0                                            # everything hits: first K
+    dist[0, 5, 3:3 + 4 * K:4] = 0.0                                # component 3 of K consecutive lanes
+    dist[0, 6, 1000:1000 + K - 1] = 0.0                            # K - 1 hits -> one cyclic repeat
+    dist[0, 7, :] = np.nan
+    dist[0, 8, 100:110] = 0.0; dist[0, 8, 105] = 7.0; dist[0, 8, 8191] = 0.0   # a gap inside a run; the last element
+    rng = np.random.default_rng(9)
+    dist[0, 9, rng.choice(N, 5 * K, replace=False)] = 0.0          # 5K hits anywhere: K reached in mid-block
+    got = run_ball_query(dist, 1.0, K)
+    np.testing.assert_array_equal(got, oracle.ball_query(dist, 1.0, K))
+    np.testing.assert_array_equal(got[0, 0, :8], [40, 41, 42, 43, 40, 41, 42, 43])
+    # a view that is not 16-byte aligned takes the scalar path: same answer
+    d = torch.from_numpy(np.concatenate([np.zeros(1, np.float32), dist.ravel()])).cuda()[1:].view(B, M, N)
+    assert d.data_ptr() % 16 != 0
+    np.testing.assert_array_equal(point_ops.ball_query_forward(d, 1.0, K).cpu().numpy(), got)
+
+
 def test_ball_query_later_quarters_stop_early(cuda):
     """Rows whose first quarter already holds K hits: later quarters stop loading once the running counts say so, and
     whatever they had collected must not leak into the output."""
