@@ -16,12 +16,6 @@
 
 namespace dib {
 
-#ifndef DIB_IM_GLOBAL_KEYS
-#define DIB_IM_GLOBAL_KEYS 0
-#endif
-#ifndef DIB_IM_PRE_SHIFT
-#define DIB_IM_PRE_SHIFT 4      // the pre-pass seeds the thresholds from the first 2^-DIB_IM_PRE_SHIFT of the row
-#endif
 constexpr int kImThreads = 128;     // 4096 (b, channel-group) CTAs' worth of work stays co-resident: no wave tail
 
 __device__ __forceinline__ uint32_t ordered_bits(float v) {
@@ -49,26 +43,15 @@ __device__ __forceinline__ void im_consider(float* bestf, unsigned long long* be
 template <int CPB, bool VEC>
 __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __restrict__ data,
                                                                const int32_t* __restrict__ index,
-                                                               int32_t* __restrict__ out, int B, int C, int N, int K,
-                                                               unsigned long long* __restrict__ gkeys) {
+                                                               int32_t* __restrict__ out, int B, int C, int N, int K) {
   extern __shared__ __align__(16) unsigned char im_smem[];
+  unsigned long long* bestk = reinterpret_cast<unsigned long long*>(im_smem);
+  float* bestv = reinterpret_cast<float*>(bestk + (size_t)CPB * K);
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * CPB;
   const int nc = min(CPB, C - c0);
-#if DIB_IM_GLOBAL_KEYS
-  // The winner keys of this CTA's (b, c0..c0+CPB) segments live in global memory (L2): the exact update is a native
-  // 64-bit RED.MAX there, where shared memory would need a compare-and-swap loop.  Only this CTA touches them.
-  unsigned long long* bestk = gkeys + ((size_t)b * C + c0) * K;
-  float* bestv = reinterpret_cast<float*>(im_smem);
-  for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = -1000.0f; }
-  __threadfence();
-  __syncthreads();
-#else
-  unsigned long long* bestk = reinterpret_cast<unsigned long long*>(im_smem);
-  float* bestv = reinterpret_cast<float*>(bestk + (size_t)CPB * K);
   for (int i = threadIdx.x; i < CPB * K; i += kImThreads) { bestk[i] = 0ull; bestv[i] = -1000.0f; }
   __syncthreads();
-#endif
   const int32_t* idx = index + (size_t)b * N;
   const float* rows = data + ((size_t)b * C + c0) * N;
 
@@ -80,7 +63,7 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
     // Every threshold is the value of a real element of its segment, so it can never exceed the
     // segment maximum, and the main pass below re-scans these elements with the full logic.
     {
-      const int npre = n4 >> DIB_IM_PRE_SHIFT;
+      const int npre = n4 >> 4;
       for (int i = threadIdx.x; i < npre; i += kImThreads) {
         const int4 kk = __ldg(reinterpret_cast<const int4*>(idx) + i);
         const int k4[4] = {kk.x, kk.y, kk.z, kk.w};
@@ -145,16 +128,9 @@ __global__ void __launch_bounds__(kImThreads) index_max_kernel(const float* __re
         if (c < nc) im_consider<CPB>(bestv, bestk, K, c, k, __ldcs(rows + (size_t)c * N + i), (uint32_t)i);
     }
   }
-#if DIB_IM_GLOBAL_KEYS
-  __threadfence();                                 // this thread's REDs before the read-back below
-  __syncthreads();
-  for (int i = threadIdx.x; i < nc * K; i += kImThreads) {
-    const unsigned long long key = __ldcg(bestk + i);
-#else
   __syncthreads();
   for (int i = threadIdx.x; i < nc * K; i += kImThreads) {
     const unsigned long long key = bestk[i];
-#endif
     out[((size_t)b * C + c0) * K + i] = key ? (int32_t)(0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull)) : 0;
   }
 }
@@ -325,31 +301,24 @@ int index_max_forward(const float* data, const int32_t* index, int32_t* out, int
   if (B == 0 || C == 0) return DIB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const bool vec = (N % 4 == 0) && ((uintptr_t)data % 16 == 0) && ((uintptr_t)index % 16 == 0);
-  const size_t per_c = (size_t)K * (DIB_IM_GLOBAL_KEYS ? 4 : 12);
+  const size_t per_c = (size_t)K * 12;
   const size_t limit = 227 * 1024;
   int cpb = 4;
   while (cpb > 1 && per_c * cpb > limit) cpb >>= 1;
   DIB_REQUIRE(per_c * cpb <= limit, "K=%d too large for the shared-memory segment table", K);
   const size_t smem = per_c * cpb;
   dim3 grid((C + cpb - 1) / cpb, B);
-  unsigned long long* gkeys = nullptr;
-#if DIB_IM_GLOBAL_KEYS
-  DIB_CHECK_CUDA(cudaMallocAsync((void**)&gkeys, (size_t)B * C * K * sizeof(unsigned long long), st));   // stream-ordered, pooled
-#endif
 #define DIB_IM_LAUNCH(CPB, VEC)                                                                              \
   do {                                                                                                       \
     auto kern = dib::index_max_kernel<CPB, VEC>;                                                             \
     DIB_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    kern<<<grid, dib::kImThreads, smem, st>>>(data, index, out, B, C, N, K, gkeys);                          \
+    kern<<<grid, dib::kImThreads, smem, st>>>(data, index, out, B, C, N, K);                                 \
   } while (0)
   if (cpb == 4) { if (vec) DIB_IM_LAUNCH(4, true); else DIB_IM_LAUNCH(4, false); }
   else if (cpb == 2) { if (vec) DIB_IM_LAUNCH(2, true); else DIB_IM_LAUNCH(2, false); }
   else { if (vec) DIB_IM_LAUNCH(1, true); else DIB_IM_LAUNCH(1, false); }
 #undef DIB_IM_LAUNCH
   DIB_CHECK_CUDA(cudaGetLastError());
-#if DIB_IM_GLOBAL_KEYS
-  DIB_CHECK_CUDA(cudaFreeAsync(gkeys, st));
-#endif
   return DIB_OK;
 }
 
