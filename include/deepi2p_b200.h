@@ -114,7 +114,8 @@ int frustum_solve_traced_f32(const float* xyz, const int8_t* label, const int32_
  * slices (frustum_solve_slice_rounds x 1024 points each) added in slice order, so that idle warps can help; the
  * variants differ at rounding level, each is deterministic.  A batch of fewer than ~4 waves of problems slices every
  * pass into short slices (slice_after 0, 2 rounds); a larger one slices only from a problem's 48th pass on, 4 rounds
- * per slice.  dib_evaluate_sliced(r) (thread-local; r = rounds per slice, 0 = one piece; default 4) selects which of
+ * per slice -- except for the problems at the last queue positions (one resident grid's worth), which start while the
+ * batch drains and use the small-batch slicing from their first pass.  dib_evaluate_sliced(r) (thread-local; r = rounds per slice, 0 = one piece; default 4) selects which of
  * them frustum_evaluate_* reproduces bit for bit. */
 int frustum_solve_slice_after(int S, int I, int is_2d, int f64_record);
 int frustum_solve_slice_rounds(int S, int I, int is_2d, int f64_record);
