@@ -1481,6 +1481,9 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
   int state = ST_FETCH;                          // warp-uniform
   bool first = true;
   int n_rec = 0;                                 // trace records written for the current problem (lane 0)
+#ifdef DIB_PASS_TIMING
+  unsigned long long t_open = global_ns();
+#endif
 
   for (;;) {
     if (state == ST_FETCH) {
@@ -1528,6 +1531,9 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         __syncwarp();
         if (lane == 0) open_pass<CT, P>(sm, me, warp);
         __syncwarp();
+#ifdef DIB_PASS_TIMING
+        t_open = global_ns();
+#endif
       }
       state = (rc == LM_EVAL) ? ST_RUN : ST_FETCH;        // lm_begin always asks for an evaluation today
       continue;
@@ -1593,6 +1599,9 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         }
         __syncwarp();
         int rc = LM_DONE;
+#ifdef DIB_PASS_TIMING
+        const unsigned long long t_complete = global_ns();
+#endif
         if (lane == 0) {
           trace_record<CT, P>(a, me, n_rec, false);
           rc = lm_consume<P>(me.lm, me.tot);
@@ -1628,6 +1637,15 @@ __global__ void __launch_bounds__(Cfg<CT, P>::kWarps * 32, DIB_CTAS_PER_SM) frus
         } else {
           state = ST_FETCH;
         }
+#ifdef DIB_PASS_TIMING
+        if (lane == 0 && a.trace != nullptr && n_rec - 1 < a.trace_cap) {
+          double* t = a.trace + ((size_t)me.prob * a.trace_cap + (n_rec - 1)) * kTraceRec;
+          const unsigned long long now = global_ns();
+          t[13] = (double)(t_complete - t_open);
+          t[14] = (double)(now - t_complete);
+          t_open = now;
+        }
+#endif
         continue;
       }
     }
