@@ -488,8 +488,9 @@ __device__ __forceinline__ bool maybe_active(float x, float y, float z, int lab,
 // loaded point by point.  (frustum_prepare_batch sorts points by (label, Morton cell) so that
 // groups are spatially compact and label-pure; unsorted clouds still work, they just cull less.)
 //
-// Global layout per sample: rounds x [8 fields][32] floats; round r holds groups 32 r .. 32 r + 31, one
-// per lane, so a warp reads consecutive words.  Fields: cx cy cz hx hy hz flags(bit0: has label 0,
+// Global layout per sample: rounds x [8 fields][32] floats; round r holds 32 groups, one per lane, so a warp reads
+// consecutive words -- groups r, r + R, r + 2R, ... of the cloud's R rounds (see frustum_boxes_kernel: every round is a
+// uniform sample of the cloud, which balances the slices of a pass).  Fields: cx cy cz hx hy hz flags(bit0: has label 0,
 // bit1: has label 1) pad.
 // ------------------------------------------------------------------------------------------
 constexpr int kBoxFields = 8;
@@ -505,7 +506,13 @@ constexpr int kBoxRoundFloats = kBoxFields * kRoundGroups;
 #ifndef DIB_SLICE_ROUNDS
 #define DIB_SLICE_ROUNDS 4                    // rounds (of 1024 points) per slice: 20480 points = 20 rounds = 5 slices
 #endif
-constexpr int kMaxSlices = 12;                // slices per pass held in shared memory (larger clouds get longer slices)
+#ifndef DIB_SMALL_SLICE_ROUNDS
+#define DIB_SMALL_SLICE_ROUNDS 2              // rounds per slice of a small batch and of the late problems of a large one
+#endif
+#ifndef DIB_MAX_SLICES
+#define DIB_MAX_SLICES 12
+#endif
+constexpr int kMaxSlices = DIB_MAX_SLICES;    // slices per pass held in shared memory (larger clouds get longer slices)
 
 __host__ __device__ inline int box_rounds(int n) { return (n + kRoundPoints - 1) / kRoundPoints; }
 // rounds per slice for a cloud of `rounds` rounds: the configured length, stretched for very large clouds so that
@@ -528,23 +535,35 @@ __global__ void __launch_bounds__(256) frustum_boxes_kernel(const CT* __restrict
                                                             const int8_t* __restrict__ label,
                                                             const int32_t* __restrict__ n_pts, int n_stride,
                                                             int rounds_max, float* __restrict__ table,
-                                                            Entry<CT>* __restrict__ packed) {
+                                                            Entry<CT>* __restrict__ packed, int interleave) {
   const int s = blockIdx.y;
   const int lane = threadIdx.x & 31;
-  const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int gid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);     // destination: slot gid % 32 of round gid / 32
   if (gid >= rounds_max * kRoundGroups) return;
   const int n = n_pts ? n_pts[s] : n_stride;
+  // Source group of this slot.  Consecutive groups of the (label, Morton)-sorted cloud are neighbours in space, and the
+  // points with a non-zero residual sit along the frustum's border: in cloud order a fifth of the rounds would hold most
+  // of a pass's exact-path work (measured: the heaviest 2-round slice has 4-6x the mean), and a pass that is cut into
+  // slices is as slow as its heaviest slice.  So round r takes groups r, r + R, r + 2R, ... (R = the cloud's rounds):
+  // every round, hence every slice, is a uniform sample of the cloud.
+  int src = gid;
+  if (interleave) {
+    const int R = box_rounds(n);
+    const int r = gid / kRoundGroups, q = gid % kRoundGroups;
+    src = (r < R) ? q * R + r : rounds_max * kRoundGroups;              // rounds beyond the cloud's own stay empty
+  }
+  const int i_src = src * 32 + lane;
   const int i = gid * 32 + lane;
   double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
   int lab = -1;
   Entry<CT> e;
   e.x = 0; e.y = 0; e.z = 0; e.lab = -1;
-  if (i < n) {
-    lab = label[(size_t)s * n_stride + i];
+  if (i_src < n) {
+    lab = label[(size_t)s * n_stride + i_src];
     if (lab == 0 || lab == 1) {
-      e.x = xyz[((size_t)s * 3 + 0) * n_stride + i];
-      e.y = xyz[((size_t)s * 3 + 1) * n_stride + i];
-      e.z = xyz[((size_t)s * 3 + 2) * n_stride + i];
+      e.x = xyz[((size_t)s * 3 + 0) * n_stride + i_src];
+      e.y = xyz[((size_t)s * 3 + 1) * n_stride + i_src];
+      e.z = xyz[((size_t)s * 3 + 2) * n_stride + i_src];
       e.lab = lab;
       lo[0] = hi[0] = (double)e.x; lo[1] = hi[1] = (double)e.y; lo[2] = hi[2] = (double)e.z;
     }
@@ -1862,7 +1881,9 @@ static int default_slice_rounds();
 // that up to 10 warps can work on one pass of a 20480-point cloud; a large one the default length (fewer slice ends).
 static int slice_rounds_for(int slice_after) {
   if (getenv("DIB_SLICE_ROUNDS")) return default_slice_rounds();
-  return slice_after == 0 ? 2 : default_slice_rounds();
+  if (slice_after != 0) return default_slice_rounds();
+  if (const char* e = getenv("DIB_SMALL_SLICE_ROUNDS")) return atoi(e) > 0 ? atoi(e) : DIB_SMALL_SLICE_ROUNDS;   // tuning knob
+  return DIB_SMALL_SLICE_ROUNDS;
 }
 
 static int default_slice_rounds() {
@@ -1882,7 +1903,8 @@ static int launch_boxes(const CT* xyz, const int8_t* label, const int32_t* n_pts
   DIB_REQUIRE(S <= 65535, "S (%d) exceeds grid.y; split the batch", S);
   const int groups = rounds_max * kRoundGroups;
   dim3 grid((groups + 7) / 8, S);
-  frustum_boxes_kernel<CT><<<grid, 256, 0, st>>>(xyz, label, n_pts, n_stride, rounds_max, table, packed);
+  static const int interleave = [] { const char* e = getenv("DIB_INTERLEAVE"); return e ? (atoi(e) != 0) : 1; }();   // tuning knob
+  frustum_boxes_kernel<CT><<<grid, 256, 0, st>>>(xyz, label, n_pts, n_stride, rounds_max, table, packed, interleave);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }
