@@ -262,7 +262,7 @@ def run_reference(args):
         "gpu_launches": 0,
         "mean_cloud_passes_per_solve": evals / float(args.steps * R * n_inits),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def make_host_batch_threads(first_id, S, n_points, threads=16):
@@ -353,8 +353,22 @@ def run_registration_config(torch, frustum, lib, dev, xyz_d, pred_d, n_points, K
             "achieved_GBps": achieved, "frac": achieved / peak, "steps": steps, "warmup": max(warmup, 1), "clocks": clocks}
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The ONE JSON line, on the process's original stdout."""
+    print(json.dumps(line), file=_JSON_OUT if _JSON_OUT is not None else sys.stdout, flush=True)
+
+
 def main():
+    global _JSON_OUT
     args = parse_args()
+    # stdout carries the JSON line and nothing else: libraries that print to file descriptor 1 (NCCL's version banner
+    # when NCCL_DEBUG is set in the environment) are sent to stderr, the line goes to a private copy of the descriptor
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
         return
@@ -374,14 +388,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # NCCL prints its version banner to stdout when NCCL_DEBUG is set; stdout carries the ONE JSON line only
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group(backend="nccl", device_id=dev)
     lib = _native.load()
     peak, peak_src = load_measured_peaks()
 
     if args.ops_only:
-        print(json.dumps({"ops": bench_ops(torch, dev, peak)}), flush=True)
+        emit({"ops": bench_ops(torch, dev, peak)})
         return
     S_local, n_inits = workload_shape(args)
     is_2d = not args.is_3d
@@ -672,7 +684,7 @@ def main():
 
     if args.ops and "configs" not in line:
         line["ops"] = bench_ops(torch, dev, peak)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
