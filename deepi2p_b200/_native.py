@@ -16,14 +16,14 @@ EXPORTS = (
     "frustum_register_workspace_bytes", "frustum_register_batch_f32",
     "frustum_evaluate_workspace_bytes",
     "frustum_evaluate_f32", "frustum_evaluate_f64", "frustum_residuals_f32", "frustum_residuals_f64",
-    "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32",
+    "frustum_prepare_workspace_bytes", "frustum_prepare_batch_f32", "frustum_sort_batch_f32",
     "frustum_inside_mask_f32", "pose_error_batch",
     "index_max_forward", "ball_query_forward", "ball_query_xyz_workspace_bytes", "ball_query_xyz_forward",
     "cluster_assign_workspace_bytes", "cluster_assign_forward",
 )
 
 
-EXPECTED_ABI = 3        # dib_abi_version() the argtypes below were written for
+EXPECTED_ABI = 4        # dib_abi_version() the argtypes below were written for
 
 
 class NativeError(RuntimeError):
@@ -102,6 +102,8 @@ def load():
     lib.frustum_prepare_batch_f32.restype = i32
     lib.frustum_prepare_batch_f32.argtypes = [vp, vp, i32, i32, i32, i32, _c.c_uint64, f64, f64, i32,
                                               vp, vp, vp, vp, vp, vp, vp, sz, vp]
+    lib.frustum_sort_batch_f32.restype = i32
+    lib.frustum_sort_batch_f32.argtypes = [vp, vp, i32, i32, i32, vp, vp, vp, vp]
     lib.frustum_inside_mask_f32.restype = i32
     lib.frustum_inside_mask_f32.argtypes = [vp, vp, i32, vp, vp, f64, f64, i32, vp, vp]
     lib.pose_error_batch.restype = i32

@@ -2133,7 +2133,7 @@ static int residuals_single(const CT* xyz, const int8_t* label, int n, int n_str
 
 extern "C" {
 
-int dib_abi_version(void) { return 3; }
+int dib_abi_version(void) { return 4; }
 const char* dib_last_error(void) { return dib::g_err; }
 
 void dib_evaluate_sliced(int rounds_per_slice) { dib::g_eval_slice_rounds = rounds_per_slice < 0 ? 0 : rounds_per_slice; }

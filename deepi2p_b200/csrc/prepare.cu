@@ -118,7 +118,7 @@ __device__ void radix_pass(const uint16_t* k16, const uint16_t* in, uint16_t* ou
 __global__ void __launch_bounds__(kPrepThreads)
     frustum_prepare_kernel(const float* __restrict__ xyz_in, const int8_t* __restrict__ pred, int n_in,
                            int n_in_stride, int n_out_stride, int I, unsigned long long seed, double ry_sigma,
-                           double t_amp, int do_sort, int n2, float* __restrict__ xyz_out,
+                           double t_amp, int do_sort, int keep_all, int n2, float* __restrict__ xyz_out,
                            int8_t* __restrict__ label_out, int32_t* __restrict__ n_pts, double* __restrict__ init,
                            double* __restrict__ init_y_angle, int32_t* __restrict__ degenerate) {
   extern __shared__ __align__(16) unsigned char prep_smem[];
@@ -146,7 +146,8 @@ __global__ void __launch_bounds__(kPrepThreads)
   for (int i = tid; i < n_in; i += kPrepThreads)
     if (lab[i] == 1) { sx += (double)px[i]; sz += (double)pz[i]; cnt += 1.0; }
   sx = block_reduce(sx, scratch, dsum); sz = block_reduce(sz, scratch, dsum); cnt = block_reduce(cnt, scratch, dsum);
-  const bool degen = !(cnt > 0.0);
+  // keep_all (frustum_sort_batch_f32): no front filter -- the caller's cloud is only reordered
+  const bool degen = !(cnt > 0.0) || keep_all != 0;
   double ang = 0.0;
   if (!degen) {
     double a = atan2(sz / cnt, sx / cnt) - 0.5 * kPi;    // registration_lsq.py:203-207
@@ -246,8 +247,8 @@ __global__ void __launch_bounds__(kPrepThreads)
   for (int i = n_front + tid; i < n_out_stride; i += kPrepThreads) { ox[i] = 0.f; oy[i] = 0.f; oz[i] = 0.f; ol[i] = -1; }
   if (tid == 0) {
     n_pts[s] = n_front;
-    init_y_angle[s] = ang;
-    degenerate[s] = degen ? 1 : 0;
+    if (init_y_angle) init_y_angle[s] = ang;
+    if (degenerate) degenerate[s] = degen ? 1 : 0;
   }
   // inits (:163-164)
   for (int i = tid; i < I; i += kPrepThreads) {
@@ -295,8 +296,32 @@ int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in,
   if (smem > 48 * 1024)
     DIB_CHECK_CUDA(cudaFuncSetAttribute(frustum_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   frustum_prepare_kernel<<<S, kPrepThreads, smem, (cudaStream_t)stream>>>(
-      xyz_in, pred, n_in, n_in_stride, n_out_stride, I, seed, ry_sigma, t_amp, do_sort, n2, xyz_out, label_out, n_pts,
+      xyz_in, pred, n_in, n_in_stride, n_out_stride, I, seed, ry_sigma, t_amp, do_sort, 0, n2, xyz_out, label_out, n_pts,
       init, init_y_angle, degenerate);
+  DIB_CHECK_CUDA(cudaGetLastError());
+  return DIB_OK;
+}
+
+// Reorder clouds by (label, Morton cell of (x, z)) WITHOUT filtering: every point is kept, labels other than 0 / 1
+// become -1 (ignored) and sort last.  For callers that hand the solver an already filtered cloud (the drop-in
+// solvePGivenK, registration.cpp:190-206): the solver's sums do not depend on the order beyond rounding, its box cull
+// does.  xyz_in [S][3][n_in_stride], label [S][n_in_stride]; xyz_out [S][3][round_up(n_in,16)], label_out, n_pts [S].
+// Clouds of more than 32768 points keep their order.
+int frustum_sort_batch_f32(const float* xyz_in, const int8_t* label, int n_in, int n_in_stride, int S, float* xyz_out,
+                           int8_t* label_out, int32_t* n_pts, dib_stream_t stream) {
+  using namespace dib;
+  DIB_REQUIRE(xyz_in && label && xyz_out && label_out && n_pts, "NULL argument");
+  DIB_REQUIRE(S >= 0 && n_in >= 0 && n_in <= n_in_stride, "bad sizes");
+  const int n_out_stride = (n_in + 15) & ~15;
+  if (S == 0) return DIB_OK;
+  const int do_sort = (n_in <= kSortMax && n_in > 1) ? 1 : 0;
+  const int n2 = (n_in + 7) & ~7;
+  const size_t smem = do_sort ? (size_t)(kPrepWarps * 128 + 128) * sizeof(uint32_t) + (size_t)3 * n2 * sizeof(uint16_t) : 0;
+  if (smem > 48 * 1024)
+    DIB_CHECK_CUDA(cudaFuncSetAttribute(frustum_prepare_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  frustum_prepare_kernel<<<S, kPrepThreads, smem, (cudaStream_t)stream>>>(
+      xyz_in, label, n_in, n_in_stride, n_out_stride, /*I=*/0, 0ull, 0.0, 0.0, do_sort, /*keep_all=*/1, n2, xyz_out,
+      label_out, n_pts, nullptr, nullptr, nullptr);
   DIB_CHECK_CUDA(cudaGetLastError());
   return DIB_OK;
 }

@@ -321,6 +321,28 @@ def prepare_batch(xyz_in, pred, n_in, n_inits, seed=0, ry_sigma=RY_SIGMA, t_amp=
     return dict(xyz=xyz, label=label, n_pts=n_pts, init=init, init_y_angle=ang, degenerate=degen)
 
 
+def sort_clouds(xyz, label, n, stream=None):
+    """Reorder clouds by (label, Morton cell of (x,z)) without filtering (frustum_sort_batch_f32): every point is kept,
+    labels other than 0 / 1 sort last as ignored.  xyz [S,3,Ns] f32 cuda, label [S,Ns] int8, n valid points per cloud.
+    Returns (xyz, label, n_pts) ready for solve_batch; the solver's sums do not depend on the order beyond rounding, its
+    box cull does."""
+    _require_cuda()
+    lib = _native.load()
+    S, Ns_in = _check_cloud(xyz, label, what="xyz", dtypes=(torch.float32,))
+    dev = xyz.device
+    if not (0 <= int(n) <= Ns_in):
+        raise ValueError("n must be within the point stride")
+    Ns = round_up(int(n), 16)
+    with torch.cuda.device(dev):
+        oxyz = torch.empty((S, 3, Ns), dtype=torch.float32, device=dev)
+        olab = torch.empty((S, Ns), dtype=torch.int8, device=dev)
+        n_pts = torch.empty((S,), dtype=torch.int32, device=dev)
+        rc = lib.frustum_sort_batch_f32(_ptr(xyz), _ptr(label), int(n), Ns_in, S, _ptr(oxyz), _ptr(olab), _ptr(n_pts),
+                                        _stream_ptr(stream))
+    _native.check(rc, "frustum_sort_batch")
+    return oxyz, olab, n_pts
+
+
 def register_batch(xyz_in, pred, n_in, K, H, W, n_inits=60, seed=0, t_lb=DEFAULT_T_LB, t_ub=DEFAULT_T_UB,
                    max_iter=500, is_2d=True, return_all=False, stream=None, out=None):
     """Batched body of registration_lsq.py:329-343 in ONE C-ABI call (frustum_register_batch_f32): initial guess,
@@ -392,7 +414,10 @@ def solve_p_given_k(points, labels, K, init_y_angle, init_T, H, W, t_xyz_lower_b
     T = np.asarray(init_T, dtype=np.float64).reshape(3)
     xyz, l8, n_pts = pack_clouds(pts, lab)
     init = torch.tensor([[[float(init_y_angle), T[0], T[1], T[2]]]], dtype=torch.float64)
-    out = solve_batch(xyz, l8, n_pts, np.asarray(K, dtype=np.float64), init, H, W, lb[:3], ub[:3], int(max_iter),
+    # the solver reads a (label, Morton)-sorted copy (its box cull needs spatially compact groups; the sums do not depend
+    # on the order beyond rounding); the residual vector below is formed from the caller's order
+    sxyz, sl8, sn = sort_clouds(xyz, l8, pts.shape[1]) if xyz.dtype == torch.float32 and pts.shape[1] > 1 else (xyz, l8, n_pts)
+    out = solve_batch(sxyz, sl8, sn, np.asarray(K, dtype=np.float64), init, H, W, lb[:3], ub[:3], int(max_iter),
                       bool(is_2d), return_all=True)
     x = out["params"][0, 0]                  # all six slots (unused ones are zero): goes to the kernel without a copy
     res = residuals(xyz[0], l8[0], pts.shape[1], np.asarray(K, dtype=np.float64), x, H, W, bool(is_2d),

@@ -165,6 +165,14 @@ int frustum_prepare_batch_f32(const float* xyz_in, const int8_t* pred, int n_in,
                               int32_t* n_pts, double* init, double* init_y_angle, int32_t* degenerate,
                               void* workspace, size_t workspace_bytes, dib_stream_t stream);
 
+/* Reorder clouds by (label, Morton cell of (x,z), original index) WITHOUT filtering: every point is kept, labels other
+ * than 0 / 1 become -1 (ignored) and sort last; clouds of more than 32768 points keep their order.  For callers that
+ * hand the solver an already filtered cloud -- the drop-in solvePGivenK (registration.cpp:190-206) sorts its cloud with
+ * this before frustum_solve_batch_f32 (the residual vector is still formed in the caller's point order).
+ * xyz_in [S][3][n_in_stride] f32, label [S][n_in_stride] int8; xyz_out [S][3][round_up(n_in,16)], label_out, n_pts [S]. */
+int frustum_sort_batch_f32(const float* xyz_in, const int8_t* label, int n_in, int n_in_stride, int S, float* xyz_out,
+                           int8_t* label_out, int32_t* n_pts, dib_stream_t stream);
+
 /* The whole per-sample body of evaluation/registration_lsq.py:329-343 in ONE call -- the batched entry point that
  * replaces the reference's fork-per-solve loop (registration_lsq.py:142-186): frustum_prepare_batch_f32 (sort on) +
  * frustum_solve_batch_f32 + arg-min + the degenerate-sample rule (no predicted-inside point: P = I, cost = 1e4,

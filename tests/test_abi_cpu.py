@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(handle, name), name
     assert set(_native.EXPORTS) <= decl | {"dib_last_error"}
     handle.dib_abi_version.restype = ctypes.c_int
-    assert handle.dib_abi_version() == 3
+    assert handle.dib_abi_version() == 4
     handle.frustum_solve_workspace_bytes.restype = ctypes.c_size_t
     handle.frustum_solve_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
     assert handle.frustum_solve_workspace_bytes(4096, 60, 20480) >= 4096 * 60 * (6 * 8 + 8 + 16)

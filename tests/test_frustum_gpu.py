@@ -226,6 +226,31 @@ def test_ragged_empty_and_ignored_labels(cuda):
     assert out["costs"][2, 0].item() == 0.0
 
 
+def test_sort_clouds_is_a_permutation(cuda):
+    """frustum_sort_batch_f32 (the drop-in's pre-sort): every point kept, labels other than 0 / 1 become -1 and sort
+    last, label 0 before label 1, and the cost at a pose is the unsorted cloud's up to summation order."""
+    S, n = 3, 3001
+    smps = [small_sample(30 + s, n) for s in range(S)]
+    pts = np.stack([s["points"] for s in smps]); prd = np.stack([s["pred"] for s in smps]).astype(np.int64)
+    prd[:, ::97] = 7                                           # some ignored labels
+    xyz, l8, n_pts = frustum.pack_clouds(pts, prd)
+    sx, sl, sn = frustum.sort_clouds(xyz, l8, n)
+    assert sn.tolist() == [n] * S and sx.shape[-1] == (n + 15) // 16 * 16
+    for s in range(S):
+        a = np.concatenate([xyz[s, :, :n].cpu().numpy().T, l8[s, :n].cpu().numpy()[:, None].astype(np.float32)], 1)
+        b = np.concatenate([sx[s, :, :n].cpu().numpy().T, sl[s, :n].cpu().numpy()[:, None].astype(np.float32)], 1)
+        assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])      # same multiset of (x, y, z, label)
+        lab = sl[s, :n].cpu().numpy()
+        cls = np.where(lab == 0, 0, np.where(lab == 1, 1, 2))
+        assert (np.diff(cls) >= 0).all()                                              # 0s, then 1s, then ignored
+        assert (sl[s, n:].cpu().numpy() == -1).all()
+    K, H, W = smps[0]["K"], smps[0]["H"], smps[0]["W"]
+    x = torch.zeros(S, 6, dtype=torch.float64, device="cuda"); x[:, 0] = 0.3; x[:, 3] = 1.0
+    c0, g0, _ = frustum.evaluate_batch(xyz, l8, n_pts, K, x, H, W, True)
+    c1, g1, _ = frustum.evaluate_batch(sx, sl, sn, K, x, H, W, True)
+    assert torch.allclose(c0, c1, rtol=1e-12, atol=0) and torch.allclose(g0, g1, rtol=1e-9, atol=1e-9)
+
+
 def test_residual_vector_and_dropin(cuda):
     import deepi2p_b200
     deepi2p_b200.install_dropins()

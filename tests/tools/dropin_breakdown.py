@@ -37,7 +37,11 @@ def main():
     xyz, l8, n_pts = frustum.pack_clouds(pts, lab)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     init = torch.tensor([[[float(ry[0]), t[0][0], t[0][1], t[0][2]]]], dtype=torch.float64)
-    for name, (a, b, c) in (("unsorted", (xyz, l8, n_pts)),):
+    sx, sl, sn = frustum.sort_clouds(xyz, l8, pts.shape[1])
+    for _ in range(3):
+        e0.record(); frustum.sort_clouds(xyz, l8, pts.shape[1]); e1.record(); sync()
+    print("sort_clouds device time %.3f ms" % e0.elapsed_time(e1))
+    for name, (a, b, c) in (("unsorted", (xyz, l8, n_pts)), ("sorted", (sx, sl, sn))):
         for _ in range(3):
             e0.record(); out = frustum.solve_batch(a, b, c, np.asarray(K, dtype=np.float64), init, H, W, syn.T_LB, syn.T_UB, 500, True, return_all=True); e1.record(); sync()
         print(name, "solve_batch device time %.3f ms, evaluations %d" % (e0.elapsed_time(e1), int(out["stats"][0, 0, 1])))
