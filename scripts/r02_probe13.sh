@@ -1,5 +1,6 @@
 #!/bin/bash
 # global board (cross-SM end-of-batch help): correctness first, then same-call A/B against DIB_GLOBAL_HELP=0
+# (ran against the experimental kernel of profiles/r02_global_board.patch, applied on commit 926bb8c; the knob is not in the shipped source)
 mkdir -p gpurun_out; rm -f gpurun_out/sweep.log
 timeout 240 python -m pytest tests/test_frustum_gpu.py -x -q 2>&1 | tail -4
 scripts/ab_prebuilt.sh "default|DIB_GLOBAL_HELP=0" "default|DIB_GLOBAL_HELP=1" "default|DIB_GLOBAL_HELP=0" "default|DIB_GLOBAL_HELP=1"
