@@ -29,6 +29,8 @@ if which in ("all", "solver"):
     xyz64, lab64, n64 = frustum.pack_clouds(pts64, smps[0]["pred"])
     o64 = frustum.solve_batch(xyz64, lab64, n64, smps[0]["K"], np.array([[[0.1, 0, 0, 1.0]]]), smps[0]["H"], smps[0]["W"])
     print("f64", o64["cost"].cpu().numpy())
+    sx, sl, sn = frustum.sort_clouds(*frustum.pack_clouds(np.stack([s["points"] for s in smps]), np.stack([s["pred"] for s in smps]))[:2], n)
+    print("sort_clouds", sn.tolist(), int((sl >= 0).sum()))
 if which in ("all", "ops"):
     data, index = syn.make_index_max_inputs(1, 2, 6, 1030, 16)
     print("index_max", point_ops.index_max_forward(torch.from_numpy(data).cuda(), torch.from_numpy(index).cuda(), 16).sum().item())
@@ -36,6 +38,8 @@ if which in ("all", "ops"):
     print("index_max vec", point_ops.index_max_forward(torch.from_numpy(data).cuda(), torch.from_numpy(index).cuda(), 32).sum().item())
     dist, radius = syn.make_ball_query_inputs(2, 2, 6, 5000, 16)
     print("ball_query split", point_ops.ball_query_forward(torch.from_numpy(dist).cuda(), radius, 16).sum().item())
+    dist, radius = syn.make_ball_query_inputs(2, 2, 6, 8192, 16)
+    print("ball_query split, 128-bit path", point_ops.ball_query_forward(torch.from_numpy(dist).cuda(), radius, 16).sum().item())
     dist, radius = syn.make_ball_query_inputs(2, 2, 6, 700, 16)
     print("ball_query warp", point_ops.ball_query_forward(torch.from_numpy(dist).cuda(), radius, 16).sum().item())
     rng = np.random.default_rng(0)
