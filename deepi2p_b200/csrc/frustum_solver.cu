@@ -5,13 +5,15 @@
 // and the multi-start loop around it (evaluation/registration_lsq.py:127-186).
 //
 // Execution model (round 2): ONE WARP owns one (cloud, labels, intrinsics, init pose) problem from its
-// first evaluation to its final pose; a CTA is a team of warps (one CTA per SM) that share nothing in the
+// first evaluation to its final pose; a CTA is a team of 10 warps (two CTAs per SM) that share nothing in the
 // steady state -- there is no CTA-wide barrier anywhere in the solve loop.  A pass over the cloud is cut
 // into a FIXED sequence of slices (a few rounds of 32 groups x 32 points each); each slice is reduced on
 // its own, in a fixed order, and the slice sums are added in slice order.  Because a slice's sum does not
 // depend on which warp computed it, warps that have run out of problems (the end-of-kernel tail, small
 // batches, the single-problem drop-in call) claim open slices of their CTA-mates' passes through shared
 // memory and the results stay bit-identical run to run and independent of who helped.
+// The cloud's 32-point groups are dealt round-robin over the rounds, so that every slice carries the same share of
+// the exact-path work (a sliced pass is as slow as its heaviest slice).
 //
 // Per slice a warp culls whole 32-point groups against the frustum with a per-launch box table,
 // classifies the points of undecided groups in fp32 with a conservative margin, evaluates the
